@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the N-body hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3              # 1 GPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...       # N GPUs, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle)
+
+A "step" is one nb_step_brute_force over the whole particle set (forces from old positions + Euler).
+Workloads (BASELINE.json configs; default c3 = the configuration the headline metric and the north-star
+target are quoted on, the 1,048,576-body all-pairs system -- it fits one GPU, and using the same fixed
+problem at every N makes the 1/2/4/8-GPU line a strong-scaling curve):
+    c2  65,536-body Plummer (2-D projection), all-pairs
+    c3  1,048,576-body Plummer, all-pairs                     [default]
+    c4  262,144-body uniform disk, Barnes-Hut theta=0.5
+    c5  4,194,304-body uniform disk, Barnes-Hut theta=0.75
+metric  = pair interactions per second, N(N-1) ordered pairs per step (rs-src/nbody.rs:108-110 evaluates both
+          directions); for the Barnes-Hut workloads the line reports body-steps/s and steps/s instead.
+value   = whole-job device throughput, state resident in HBM, CUDA events, max over ranks.
+e2e     = the same steps through the reference-facing C ABI with HOST buffers: every step does
+          nb_set_particles (H2D from pinned memory) + nb_step_* + nb_get_particles (D2H), wall clock.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 12  # <2,REF>: 2 sub + 2 FMA + rcp + mul + 2 FMA
+WORKLOADS = {
+    "c2": dict(n=65536, kind="allpairs", ic="plummer", seed=2, desc="65,536-body Plummer (2-D), all-pairs"),
+    "c3": dict(n=1 << 20, kind="allpairs", ic="plummer", seed=3, desc="1,048,576-body Plummer (2-D), all-pairs"),
+    "c4": dict(n=262144, kind="bh", theta=0.5, ic="disk", seed=4, desc="262,144-body uniform disk, Barnes-Hut theta=0.5"),
+    "c5": dict(n=1 << 22, kind="bh", theta=0.75, ic="disk", seed=5, desc="4,194,304-body uniform disk, Barnes-Hut theta=0.75"),
+}
+DT = 0.01
+
+
+def make_ic(w):
+    from rust_exp_b200 import ic
+
+    if w["ic"] == "plummer":
+        return ic.plummer_2d(w["n"], seed=w["seed"])
+    return ic.random_disk(w["n"], seed=w["seed"])
+
+
+def peaks():
+    p = {}
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            inside = t0 - 0.05 <= t <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                    for nm, v in zip(names, f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(nm)
+            except ValueError:
+                pass
+        if not sm:  # region shorter than the sampling period: use everything we saw
+            for t, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_allpairs(state, seconds=12.0, all_cores=True):
+    """The reference's CPU all-pairs force loop (oracle restatement, rs-src/nbody.rs:132-144, ONE thread as
+    in the reference) on a bounded sample of rows of the same particle set."""
+    import oracle
+
+    o = oracle.get()
+    o.set_particles(state)
+    n = state.shape[0]
+    t = time.perf_counter(); o.brute_forces_rows(0, min(n, 8)); probe = (time.perf_counter() - t) / min(n, 8)
+    rows = int(max(8, min(n, seconds / max(probe, 1e-9))))
+    t = time.perf_counter(); o.brute_forces_rows(0, rows); dt = time.perf_counter() - t
+    out = {"value": rows * (n - 1) / dt, "unit": "pair-interactions/s", "cores": 1, "kind": "port",
+           "sample": f"forces on the first {rows} of {n} bodies against all {n} (rs-src/nbody.rs:132-144, single thread as in the reference), {dt:.1f} s"}
+    if all_cores:
+        nc = os.cpu_count() or 1
+        rows2 = min(n, rows * nc // 2)
+        t = time.perf_counter(); o.brute_forces_rows(0, rows2, nthreads=nc); dt2 = time.perf_counter() - t
+        out["all_cores_not_in_reference"] = {"value": rows2 * (n - 1) / dt2, "cores": nc,
+                                             "note": "i loop split over host threads; the reference's brute force is single-threaded"}
+    return out
+
+
+def cpu_baseline_bh(state, theta, seconds=12.0):
+    import oracle
+
+    o = oracle.get()
+    nc = os.cpu_count() or 1
+    o.set_particles(state)
+    t = time.perf_counter(); o.step_barnes_hut(theta, DT, nc); dt = time.perf_counter() - t
+    steps = 1
+    while dt < seconds / 3 and steps < 4:
+        t = time.perf_counter(); o.step_barnes_hut(theta, DT, nc); dt = min(dt, time.perf_counter() - t); steps += 1
+    n = state.shape[0]
+    return {"value": n / dt, "unit": "body-steps/s", "cores": nc, "kind": "port", "steps_per_s": 1.0 / dt,
+            "sample": f"{steps} full nb_step_barnes_hut steps of {n} bodies, nthreads={nc} (serial tree build + threaded walk, rs-src/nbody.rs:413-478), best step {dt:.2f} s"}
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference is
+    Rust and cannot be built in this image), timed on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+
+    o = oracle.get()
+    state = make_ic(w)
+    n = w["n"]
+    o.set_particles(state)
+    nc = os.cpu_count() or 1
+    if w["kind"] == "allpairs":
+        # bounded sample per step: rows sized for ~2 s of single-thread work
+        t = time.perf_counter(); o.brute_forces_rows(0, 8); probe = (time.perf_counter() - t) / 8
+        rows = int(max(8, min(n, 2.0 / probe)))
+        for _ in range(args.warmup):
+            o.brute_forces_rows(0, max(8, rows // 8))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            o.brute_forces_rows(0, rows)
+        el = time.perf_counter() - t0
+        value, unit, cores = rows * (n - 1) * args.steps / el, "pair-interactions/s", 1
+        sample = f"per step: forces on {rows} of {n} bodies against all {n}, single thread (the reference's brute force is single-threaded)"
+        metric = "pair-interactions/s"
+    else:
+        for _ in range(min(args.warmup, 1)):
+            o.step_barnes_hut(w["theta"], DT, nc)
+        k = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            o.step_barnes_hut(w["theta"], DT, nc)
+        el = time.perf_counter() - t0
+        value, unit, cores = n * k / el, "body-steps/s", nc
+        sample = f"{k} full Barnes-Hut steps, nthreads={nc}"
+        metric = "body-steps/s"
+        args.steps = k
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['desc']}", "dt": DT},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("NB_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--transport", default=os.environ.get("NB_TRANSPORT", "p2p_direct"),
+                    choices=["p2p_direct", "p2p_gather", "nccl"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bodies-per-thread", type=int, default=0)
+    ap.add_argument("--waves", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+
+    import torch
+    import torch.distributed as dist
+
+    import rust_exp_b200 as pkg
+    from rust_exp_b200 import binding
+    from rust_exp_b200 import dist as nbdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- libnbody_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+
+    lib = pkg.load()
+    lib.init(local_rank)
+    stream = torch.cuda.current_stream()
+    lib.set_stream(stream.cuda_stream)  # torch CUDA events then bracket the library's launches
+    lib.tune(args.bodies_per_thread, args.waves, args.ctas_per_sm)
+    n = w["n"]
+    transport = {"p2p_direct": 0, "p2p_gather": 1, "nccl": 2}[args.transport]
+    if world > 1:
+        nbdist.wire(lib, n, transport)
+
+    # pinned host state (the e2e leg copies from / to it every step)
+    host = torch.empty((n, 5), dtype=torch.float32, pin_memory=True)
+    host.numpy()[:] = make_ic(w)
+    host_out = torch.empty((n, 5), dtype=torch.float32, pin_memory=True)
+    lib.set_particles(host.numpy())
+
+    def step():
+        if w["kind"] == "allpairs":
+            lib.step_brute_force(DT)
+        else:
+            lib.step_barnes_hut(w["theta"], DT, 1)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+        flush.zero_()
+    barrier()
+
+    lib.reset_counters()
+    lib.phase_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        flush.zero_()  # L2 flush between timed iterations (inside the timed region; ~0.1 ms each)
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop(t0, t1)
+    phases = lib.phase_ms()
+    lib.phase_timing(False)
+    ctr = lib.counters()
+    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+    launches = torch.tensor([ctr["kernel_launches"]], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(launches)
+    ms_per_step = ms / args.steps
+
+    # ---- e2e through the C ABI with host buffers ---------------------------------------------------
+    e2e_steps = max(1, args.e2e_steps)
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lib.set_particles(host.numpy())        # H2D (each rank uploads its shard of the pinned array)
+        step()
+        lib.get_particles(host_out.numpy())    # D2H of the full state (synchronises)
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item()) / e2e_steps
+    b, c = lib.dist_local_range() if world > 1 else (0, n)
+    h2d = torch.tensor([20 * c], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(h2d)
+    d2h = 20 * n * world
+
+    pk = peaks()
+    sm_max = pk.get("sm_max_mhz", 1965.0)
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak = 2 * 128 * sms * sm_max * 1e6 / 1e12  # TFLOP/s, SURVEY.md H9
+
+    if w["kind"] == "allpairs":
+        pairs_per_step = n * (n - 1)
+        value = pairs_per_step * args.steps / (ms * 1e-3)
+        e2e_value = pairs_per_step / e2e_s
+        metric, unit = "pair-interactions/s", "pair-interactions/s"
+        force_ms = phases["force"]
+        # dominant kernel = allpairs_fast_kernel: each rank's launch evaluates n_local*(n-1) pairs
+        per_launch_pairs = (n // world) * (n - 1)
+        achieved = per_launch_pairs * FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
+        roofline = {"bound": "fp32", "kernel": "allpairs_fast_kernel", "achieved": achieved, "peak": fp32_peak,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+                    "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": force_ms, "kernel_share_of_step": force_ms / ms_per_step,
+                    "peak_source": f"computed 2*128*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; sm_max_mhz is from it); "
+                                   "the kernel is co-limited by the MUFU pipe at 75% of this (DESIGN.md section 4)",
+                    "mufu_bound_frac": (achieved / (0.75 * fp32_peak)) if achieved else None}
+        extra = {"fp32_tflops": value * FLOP_PER_PAIR / 1e12, "fp32_frac_of_peak_all_gpus": value * FLOP_PER_PAIR / 1e12 / (fp32_peak * world)}
+    else:
+        value = n * args.steps / (ms * 1e-3)
+        e2e_value = n / e2e_s
+        metric, unit = "body-steps/s", "body-steps/s"
+        roofline = {"bound": "hbm", "kernel": "bh_traverse", "achieved": None, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                    "frac": None, "traffic": None}
+        extra = {"bh_steps_per_s": args.steps / (ms * 1e-3)}
+
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "n_bodies": n, "dt": DT, "mode": "fast",
+                   "parallelism": f"index-sharded x{world}" + (f", transport={args.transport}" if world > 1 else ""),
+                   "l2": "flushed between timed steps (256 MiB memset inside the timed region); the 12 MiB position set is re-read from L2 by design",
+                   "ic": w["ic"], "seed": w["seed"]},
+        "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "what": "nb_set_particles(pinned host AoS) + nb_step + nb_get_particles(pinned host AoS), wall clock, max over ranks"},
+        "gpu_launches": int(launches.item()),
+        "clocks": clocks,
+        "roofline": roofline,
+        "phases_ms": phases,
+    }
+    line.update(extra)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        st = host.numpy().copy()
+        line["cpu_baseline"] = cpu_baseline_allpairs(st) if w["kind"] == "allpairs" else cpu_baseline_bh(st, w["theta"])
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

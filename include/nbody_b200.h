@@ -1,0 +1,151 @@
+/*
+ * nbody_b200.h -- C ABI of libnbody_b200.so, the B200-native replacement for the N-body hot path of
+ * blitzcode/rust-exp (rs-src/nbody.rs).
+ *
+ * The six nb_* symbols below are exactly the `#[no_mangle] pub extern fn` surface that
+ * hs-src/RustNBodyExperiment.hs:101-106 binds with `foreign import ccall`; names, argument order,
+ * C types and (void) error behaviour are the reference's.  State is a hidden process-global particle
+ * set that survives between calls (rs-src/nbody.rs:28-32), here resident in GPU HBM.
+ *
+ * Two further nb_* symbols are REQUIRED ADDITIONS (the reference has no state getter/setter and seeds
+ * its initial conditions from an unseeded RNG, so parity cannot be tested without them).
+ *
+ * Everything prefixed nbx_ is an extension surface (device selection, bit-exact mode, stream
+ * injection, multi-GPU wiring, counters).  None of it is needed for single-GPU drop-in use.
+ *
+ * Error behaviour: the reference panics across the FFI boundary (rs-src/nbody.rs:231,246,267,...);
+ * the nb_* functions return void, so on an unrecoverable CUDA error they print to stderr and abort().
+ * nbx_* functions return 0 on success and a negative code on failure (message in nbx_last_error()).
+ * There is NO CPU fallback: every entry point that computes requires a CUDA device.
+ */
+#ifndef NBODY_B200_H
+#define NBODY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Reference surface (drop-in).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* rs-src/nbody.rs:34-37.  Number of particles in the global set (all ranks' particles when sharded). */
+int32_t nb_num_particles(void);
+
+/* rs-src/nbody.rs:39-64.  Replace the set with n particles uniformly placed in a disk of radius 23,
+ * v in [-3.5,3.5)^2, m in [0.1,1.5).  Distribution-level match only (the reference RNG is unseeded);
+ * generated on the device from a counter-based RNG seeded by nbx_seed(). */
+void nb_random_disk(int32_t num_particles);
+
+/* rs-src/nbody.rs:73-104.  Sun (m=1000, at rest at the origin) + n-1 unit-mass planets on circular
+ * orbits with r in [rmin,rmax), speed sqrt(1000) independent of r (2-D log-potential gravity). */
+void nb_stable_orbits(int32_t num_particles, float rmin, float rmax);
+
+/* rs-src/nbody.rs:106-162.  One O(N^2) step: forces from OLD positions, then v += (dt*F)/m,
+ * p += dt*v.  Asynchronous on the library stream; any nb_get/nb_draw/nbx_synchronize orders after it. */
+void nb_step_brute_force(float dt);
+
+/* rs-src/nbody.rs:186-480.  NOTE argument order: theta first.  theta == 0.0 is the brute-force step
+ * (and then no velocity kill, rs-src/nbody.rs:197-200).  Otherwise: tight non-square AABB, quadtree
+ * over old positions, per-body tree force with opening test (x2-x1)/d < theta, Euler, then
+ * v = 0 for bodies with |px| > 55 or |py| > 55 (rs-src/nbody.rs:466-471).
+ * nthreads is the reference's CPU thread-count hint (UI range 1..16): accepted and ignored, except
+ * that nthreads <= 0 aborts like the reference's division by zero at rs-src/nbody.rs:426. */
+void nb_step_barnes_hut(float theta, float dt, int32_t nthreads);
+
+/* rs-src/nbody.rs:482-583.  Render into the caller-owned w*h ABGR8 framebuffer `fb` (HOST memory, a
+ * mapped GL PBO in the reference host, hs-src/FrameBuffer.hs:127-135).  The image is composed on the
+ * device and written to fb with one contiguous copy; fb is never read. */
+void nb_draw(int32_t w, int32_t h, uint32_t *fb);
+
+/* ------------------------------------------------------------------------------------------------
+ * Required additions: inject / read back state.  AoS records of 5 floats
+ * {px,py,vx,vy,m}, 20-byte stride, the field order of `struct Particle` (rs-src/nbody.rs:19-26).
+ * Host pointers.  When sharded, every rank passes the same full array to nb_set_particles and
+ * nb_get_particles returns the full, gathered state on every rank.
+ * ---------------------------------------------------------------------------------------------- */
+void nb_set_particles(const float *aos5, int32_t n);
+void nb_get_particles(float *aos5_out, int32_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Extension surface.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bind the library to a CUDA device (default: device 0 on first use).  Returns 0, or <0 if no usable
+ * sm_100 device exists -- there is no CPU fallback. */
+int32_t nbx_init(int32_t device);
+void nbx_shutdown(void);
+const char *nbx_last_error(void);
+const char *nbx_version(void);
+
+/* Arithmetic mode.  FAST (default): throughput kernels (packed-FP32 FMA + MUFU.RCP, tiled sums).
+ * EXACT: every operation is a separately rounded IEEE binary32 op in the reference's order
+ * (sequential ascending-j accumulation, (m1*m2)/(d2+EPS), true division, nested tree sums) and the
+ * result is bit-identical to the CPU restatement of rs-src/nbody.rs. */
+#define NBX_MODE_FAST 0
+#define NBX_MODE_EXACT 1
+int32_t nbx_set_mode(int32_t mode);
+int32_t nbx_get_mode(void);
+
+/* Launch all work on a caller-owned cudaStream_t (e.g. the host framework's current stream) so the
+ * caller's CUDA events bracket it.  NULL restores the library's own stream. */
+int32_t nbx_set_stream(void *cuda_stream);
+int32_t nbx_synchronize(void);
+
+/* Seed for nb_random_disk / nb_stable_orbits. */
+void nbx_seed(uint64_t seed);
+
+/* Kernel-level tuning knobs (0 = library default): bodies per thread of the all-pairs kernel,
+ * target waves of work items, resident CTAs per SM. */
+int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_per_sm);
+
+/* Counters since the last reset: kernels launched by this library, pair interactions evaluated by the
+ * all-pairs path, Barnes-Hut interactions and visited nodes (the latter two only when counting is on). */
+typedef struct nbx_counters {
+    uint64_t kernel_launches;
+    uint64_t allpairs_pairs;
+    uint64_t bh_interactions;
+    uint64_t bh_nodes_visited;
+    uint64_t bh_nodes_built;
+    uint64_t steps;
+} nbx_counters;
+void nbx_get_counters(nbx_counters *out);
+void nbx_reset_counters(void);
+int32_t nbx_bh_count_interactions(int32_t enable);
+
+/* Device time (ms, CUDA events on the library stream) of the phases of the most recent step:
+ * [0] all-pairs / traversal kernel  [1] integrate  [2] aabb  [3] keys  [4] sort  [5] tree build
+ * [6] centre-of-mass  [7] cross-rank wait/gather.  Only recorded when enabled (adds event overhead). */
+#define NBX_NUM_PHASES 8
+int32_t nbx_phase_timing(int32_t enable);
+int32_t nbx_get_phase_ms(float *out8);
+
+/* Accelerations only (no state update) of the current set with the current mode, a_i = F_i / m_i in
+ * the reference's units, written to a HOST array of 2*n floats.  Used by sampled parity checks. */
+int32_t nbx_accelerations(float *axy_out, int32_t n);
+
+/* ---- multi-GPU (one process per GPU; particles shard by index) -------------
+ * Wiring is done by the host framework's process group (torch.distributed in this repo):
+ *   1. every rank: nbx_dist_init(rank, world, max_particles) -> allocates the symmetric arena
+ *   2. every rank: nbx_dist_export(handle)  ; all-gather the 64-byte handles ; nbx_dist_import(all)
+ *   3. (NCCL transport only) rank 0: nbx_dist_nccl_unique_id ; broadcast ; all: nbx_dist_nccl_init
+ * After that nb_set_particles / nb_step_* / nb_get_particles are collective calls.
+ */
+#define NBX_TRANSPORT_P2P_DIRECT 0 /* all-pairs kernel TMA-loads j tiles straight from peer HBM over NVLink */
+#define NBX_TRANSPORT_P2P_GATHER 1 /* pull kernel copies peer shards into local HBM, then local kernel */
+#define NBX_TRANSPORT_NCCL 2       /* ncclAllGather baseline */
+int32_t nbx_dist_init(int32_t rank, int32_t world, int32_t max_particles);
+int32_t nbx_dist_handle_bytes(void);
+int32_t nbx_dist_export(void *handle_out);
+int32_t nbx_dist_import(const void *all_handles, int32_t world);
+int32_t nbx_dist_nccl_unique_id(void *id_out128);
+int32_t nbx_dist_nccl_init(const void *id128);
+int32_t nbx_dist_set_transport(int32_t transport);
+int32_t nbx_dist_local_range(int32_t *begin, int32_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_B200_H */

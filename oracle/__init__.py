@@ -1,0 +1,152 @@
+"""ctypes loader for the CPU oracle (oracle/nbody_oracle.c).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (rust_exp_b200) never imports this.
+
+Parity status: unpinned by reference vectors (the reference has none and cannot be built here);
+see the header of nbody_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "nbody_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s", "liboracle.so"])
+    return _SO
+
+
+class Oracle:
+    """Thin typed wrapper over liboracle.so; one process-global particle set, like the reference."""
+
+    def __init__(self) -> None:
+        build()
+        L = C.CDLL(_SO)
+        f, i32, vp = C.c_float, C.c_int32, C.c_void_p
+        L.ora_num_particles.restype = i32
+        L.ora_set_particles.argtypes = [vp, i32]
+        L.ora_get_particles.argtypes = [vp, i32]
+        L.ora_seed.argtypes = [C.c_uint64]
+        L.ora_random_disk.argtypes = [i32]
+        L.ora_stable_orbits.argtypes = [i32, f, f]
+        L.ora_force.argtypes = [f, f, f, f, f, f, vp]
+        L.ora_brute_forces_rows.argtypes = [i32, i32, vp]
+        L.ora_brute_forces_rows_mt.argtypes = [i32, i32, vp, i32]
+        L.ora_step_brute_force.argtypes = [f]
+        L.ora_step_barnes_hut.argtypes = [f, f, i32]
+        L.ora_bh_build.argtypes = []
+        L.ora_bh_node_count.restype = i32
+        L.ora_bh_max_depth.restype = i32
+        L.ora_bh_flatten.argtypes = [vp, i32]
+        L.ora_bh_flatten.restype = i32
+        L.ora_bh_forces_rows.argtypes = [f, i32, i32, vp]
+        L.ora_bh_count.argtypes = [f, vp, vp]
+        L.ora_accel_f64_rows.argtypes = [vp, i32, vp]
+        L.ora_draw.argtypes = [i32, i32, vp]
+        L.ora_rgb_to_abgr32.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, f]
+        L.ora_rgb_to_abgr32.restype = C.c_uint32
+        L.ora_add_abgr32.argtypes = [C.c_uint32, C.c_uint32]
+        L.ora_add_abgr32.restype = C.c_uint32
+        self.L = L
+
+    # -- state ------------------------------------------------------------------------------
+    def num_particles(self) -> int:
+        return int(self.L.ora_num_particles())
+
+    def set_particles(self, aos: np.ndarray) -> None:
+        a = np.ascontiguousarray(aos, dtype=np.float32).reshape(-1, 5)
+        self.L.ora_set_particles(a.ctypes.data, a.shape[0])
+
+    def get_particles(self) -> np.ndarray:
+        n = self.num_particles()
+        out = np.empty((n, 5), dtype=np.float32)
+        self.L.ora_get_particles(out.ctypes.data, n)
+        return out
+
+    def seed(self, s: int) -> None:
+        self.L.ora_seed(s)
+
+    def random_disk(self, n: int) -> None:
+        self.L.ora_random_disk(n)
+
+    def stable_orbits(self, n: int, rmin: float, rmax: float) -> None:
+        self.L.ora_stable_orbits(n, rmin, rmax)
+
+    # -- all pairs --------------------------------------------------------------------------
+    def force(self, p1, m1, p2, m2) -> np.ndarray:
+        out = np.empty(2, dtype=np.float32)
+        self.L.ora_force(p1[0], p1[1], m1, p2[0], p2[1], m2, out.ctypes.data)
+        return out
+
+    def brute_forces_rows(self, i0: int, i1: int, nthreads: int = 1) -> np.ndarray:
+        out = np.empty((i1 - i0, 2), dtype=np.float32)
+        if nthreads == 1:
+            self.L.ora_brute_forces_rows(i0, i1, out.ctypes.data)
+        else:
+            self.L.ora_brute_forces_rows_mt(i0, i1, out.ctypes.data, nthreads)
+        return out
+
+    def step_brute_force(self, dt: float) -> None:
+        self.L.ora_step_brute_force(dt)
+
+    # -- Barnes-Hut -------------------------------------------------------------------------
+    def step_barnes_hut(self, theta: float, dt: float, nthreads: int = 1) -> None:
+        self.L.ora_step_barnes_hut(theta, dt, nthreads)
+
+    def bh_build(self) -> None:
+        self.L.ora_bh_build()
+
+    def bh_node_count(self) -> int:
+        return int(self.L.ora_bh_node_count())
+
+    def bh_max_depth(self) -> int:
+        return int(self.L.ora_bh_max_depth())
+
+    def bh_flatten(self) -> np.ndarray:
+        n = self.bh_node_count()
+        out = np.empty((n, 9), dtype=np.float32)
+        got = self.L.ora_bh_flatten(out.ctypes.data, n)
+        assert got == n, (got, n)
+        return out
+
+    def bh_forces_rows(self, theta: float, i0: int, i1: int) -> np.ndarray:
+        out = np.empty((i1 - i0, 2), dtype=np.float32)
+        self.L.ora_bh_forces_rows(theta, i0, i1, out.ctypes.data)
+        return out
+
+    def bh_count(self, theta: float) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.L.ora_bh_count(theta, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    # -- f64 helper -------------------------------------------------------------------------
+    def accel_f64_rows(self, rows: np.ndarray) -> np.ndarray:
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        out = np.empty((r.shape[0], 2), dtype=np.float64)
+        self.L.ora_accel_f64_rows(r.ctypes.data, r.shape[0], out.ctypes.data)
+        return out
+
+    # -- draw -------------------------------------------------------------------------------
+    def draw(self, w: int, h: int) -> np.ndarray:
+        fb = np.empty((h, w), dtype=np.uint32)
+        self.L.ora_draw(w, h, fb.ctypes.data)
+        return fb
+
+
+_singleton: Oracle | None = None
+
+
+def get() -> Oracle:
+    global _singleton
+    if _singleton is None:
+        _singleton = Oracle()
+    return _singleton

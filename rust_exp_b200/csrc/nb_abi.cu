@@ -1,0 +1,288 @@
+// nb_abi.cu -- the extern "C" surface of libnbody_b200.so (include/nbody_b200.h).
+//
+// The six reference symbols keep the exact names / argument order / C types that
+// hs-src/RustNBodyExperiment.hs:101-106 imports from rs-src/nbody.rs; each takes the engine mutex for
+// the whole call, like the reference's PARTICLES.lock() (rs-src/nbody.rs:36,43,82,117,380,517).
+// No C++ exception crosses this boundary: everything below is noexcept-by-construction (abort on error).
+#include <string.h>
+
+#include "nb_engine.h"
+
+using namespace nb;
+
+#define NB_LOCK() std::lock_guard<std::mutex> lock__(engine().mu)
+
+static void replace_set_begin(Engine& e, int n) {
+    ensure_init(e);
+    if (n < 0) n = 0;
+    if (e.dist && e.world > 1) dist_wait_all(e, e.step_count);  // peers may still be reading our arena
+    e.n = n;
+    ensure_capacity(e, n);
+}
+static void replace_set_end(Engine& e) {
+    if (e.dist && e.world > 1) {
+        e.step_count++;
+        dist_signal_step_done(e);
+    }
+}
+
+extern "C" {
+
+// rs-src/nbody.rs:34-37
+int32_t nb_num_particles(void) {
+    NB_LOCK();
+    return engine().n;
+}
+
+// rs-src/nbody.rs:39-64
+void nb_random_disk(int32_t num_particles) {
+    NB_LOCK();
+    Engine& e = engine();
+    replace_set_begin(e, num_particles);
+    generate_random_disk(e, e.n);
+    replace_set_end(e);
+}
+
+// rs-src/nbody.rs:73-104
+void nb_stable_orbits(int32_t num_particles, float rmin, float rmax) {
+    NB_LOCK();
+    Engine& e = engine();
+    // the reference always pushes the sun, then num_particles-1 planets (rs-src/nbody.rs:93-95)
+    replace_set_begin(e, num_particles < 1 ? 1 : num_particles);
+    generate_stable_orbits(e, e.n, rmin, rmax);
+    replace_set_end(e);
+}
+
+// rs-src/nbody.rs:106-162
+void nb_step_brute_force(float dt) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    step_brute_force(e, dt);
+}
+
+// rs-src/nbody.rs:186-480 -- theta first
+void nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    if (theta == 0.0f) {  // rs-src/nbody.rs:197-200 (before nthreads is ever used)
+        step_brute_force(e, dt);
+        return;
+    }
+    if (nthreads <= 0) fatal("nb_step_barnes_hut: nthreads must be >= 1 (the reference divides by it)", __FILE__, __LINE__);
+    bh_step(e, theta, dt);
+}
+
+// rs-src/nbody.rs:482-583
+void nb_draw(int32_t w, int32_t h, uint32_t* fb) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    draw_to_host(e, w, h, fb);
+}
+
+// ---- required additions ---------------------------------------------------------------------------
+void nb_set_particles(const float* aos5, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    replace_set_begin(e, n);
+    state_upload_aos(e, aos5, e.n);
+    replace_set_end(e);
+}
+
+void nb_get_particles(float* aos5_out, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    if (e.dist && e.world > 1) dist_wait_all(e, e.step_count);
+    state_download_aos(e, aos5_out, n);
+    if (e.dist && e.world > 1) {
+        e.step_count++;
+        dist_signal_step_done(e);
+    }
+}
+
+// ---- extension surface ----------------------------------------------------------------------------
+int32_t nbx_init(int32_t device) {
+    NB_LOCK();
+    return try_init(engine(), device);
+}
+
+void nbx_shutdown(void) {
+    NB_LOCK();
+    Engine& e = engine();
+    if (!e.inited) return;
+    cudaSetDevice(e.device);
+    cudaStreamSynchronize(e.stream);
+    dist_shutdown(e);
+    bh_shutdown(e);
+    if (e.arena.base) cudaFree(e.arena.base);
+    if (e.mirror) cudaFree(e.mirror);
+    if (e.partial) cudaFree(e.partial);
+    if (e.force) cudaFree(e.force);
+    if (e.work_counter) cudaFree(e.work_counter);
+    if (e.stage_dev) cudaFree(e.stage_dev);
+    if (e.stage_host) cudaFreeHost(e.stage_host);
+    for (int p = 0; p < NBX_NUM_PHASES; p++)
+        for (int k = 0; k < Engine::kPhaseRing; k++)
+            for (int j = 0; j < 2; j++)
+                if (e.ev[p][k][j]) {
+                    cudaEventDestroy(e.ev[p][k][j]);
+                    e.ev[p][k][j] = nullptr;
+                }
+    if (e.own_stream) cudaStreamDestroy(e.own_stream);
+    (void)cudaGetLastError();
+    // reset to a fresh engine (keep the mutex)
+    e.inited = false;
+    e.arena.base = nullptr; e.mirror = nullptr; e.partial = nullptr; e.force = nullptr; e.work_counter = nullptr;
+    e.stage_dev = nullptr; e.stage_host = nullptr; e.own_stream = nullptr; e.stream = nullptr;
+    e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = e.stage_host_cap = 0;
+    e.lay = ArenaLayout(); e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
+    e.cur = 0; e.step_count = 0; e.mode = NBX_MODE_FAST; e.tune = Tuning(); e.ctr = nbx_counters{};
+}
+
+const char* nbx_last_error(void) { return last_error(); }
+const char* nbx_version(void) { return "nbody_b200 0.1 (sm_100a)"; }
+
+int32_t nbx_set_mode(int32_t mode) {
+    NB_LOCK();
+    if (mode != NBX_MODE_FAST && mode != NBX_MODE_EXACT) {
+        set_error("unknown mode %d", mode);
+        return -1;
+    }
+    engine().mode = mode;
+    return 0;
+}
+int32_t nbx_get_mode(void) {
+    NB_LOCK();
+    return engine().mode;
+}
+
+int32_t nbx_set_stream(void* cuda_stream) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    e.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e.own_stream;
+    return 0;
+}
+
+int32_t nbx_synchronize(void) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    cudaError_t err = cudaStreamSynchronize(e.stream);
+    if (err != cudaSuccess) {
+        set_error("cudaStreamSynchronize: %s", cudaGetErrorString(err));
+        return -1;
+    }
+    return 0;
+}
+
+void nbx_seed(uint64_t seed) {
+    NB_LOCK();
+    engine().seed = seed;
+}
+
+int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_per_sm) {
+    NB_LOCK();
+    Engine& e = engine();
+    if (!(bodies_per_thread == 0 || bodies_per_thread == 1 || bodies_per_thread == 2 || bodies_per_thread == 4)) {
+        set_error("bodies_per_thread must be 0, 1, 2 or 4");
+        return -1;
+    }
+    e.tune.bodies_per_thread = bodies_per_thread;
+    e.tune.target_waves = target_waves;
+    e.tune.ctas_per_sm = ctas_per_sm;
+    return 0;
+}
+
+void nbx_get_counters(nbx_counters* out) {
+    NB_LOCK();
+    *out = engine().ctr;
+}
+void nbx_reset_counters(void) {
+    NB_LOCK();
+    engine().ctr = nbx_counters{};
+}
+int32_t nbx_bh_count_interactions(int32_t enable) {
+    NB_LOCK();
+    engine().bh_count = enable != 0;
+    return 0;
+}
+
+int32_t nbx_phase_timing(int32_t enable) {
+    NB_LOCK();
+    Engine& e = engine();
+    e.phase_timing = enable != 0;
+    e.ev_slot = 0;
+    for (int p = 0; p < NBX_NUM_PHASES; p++) e.ev_count[p] = 0;
+    return 0;
+}
+int32_t nbx_get_phase_ms(float* out8) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    collect_phase_times(e);
+    memcpy(out8, e.phase_ms, sizeof(float) * NBX_NUM_PHASES);
+    return 0;
+}
+
+int32_t nbx_accelerations(float* axy_out, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    if (e.n == 0 || n <= 0) return 0;
+    accelerations_local(e);
+    // each rank returns its own rows at their global position; other rows are left untouched
+    const int b = local_begin(e), c0 = local_count(e);
+    int c = c0;
+    if (b + c > n) c = n - b;
+    if (c > 0)
+        NB_CUDA(cudaMemcpyAsync(axy_out + 2 * static_cast<size_t>(b), e.force, sizeof(float2) * c, cudaMemcpyDeviceToHost,
+                                e.stream));
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    return 0;
+}
+
+int32_t nbx_dist_init(int32_t rank, int32_t world, int32_t max_particles) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    return dist_init(e, rank, world, max_particles);
+}
+int32_t nbx_dist_handle_bytes(void) { return 64; }
+int32_t nbx_dist_export(void* handle_out) {
+    NB_LOCK();
+    return dist_export(engine(), handle_out);
+}
+int32_t nbx_dist_import(const void* all_handles, int32_t world) {
+    NB_LOCK();
+    return dist_import(engine(), all_handles, world);
+}
+int32_t nbx_dist_nccl_unique_id(void* id_out128) { return dist_nccl_unique_id(id_out128); }
+int32_t nbx_dist_nccl_init(const void* id128) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    return dist_nccl_init(e, id128);
+}
+int32_t nbx_dist_set_transport(int32_t transport) {
+    NB_LOCK();
+    if (transport < 0 || transport > 2) {
+        set_error("unknown transport %d", transport);
+        return -1;
+    }
+    engine().transport = transport;
+    return 0;
+}
+int32_t nbx_dist_local_range(int32_t* begin, int32_t* count) {
+    NB_LOCK();
+    Engine& e = engine();
+    *begin = local_begin(e);
+    *count = local_count(e);
+    return 0;
+}
+
+}  // extern "C"

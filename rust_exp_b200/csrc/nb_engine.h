@@ -1,0 +1,205 @@
+// nb_engine.h -- host-side engine behind the nb_* C ABI: device-resident particle state, step
+// sequencing, multi-GPU wiring.  Mirrors the role of the process-global PARTICLES vector of the
+// reference (rs-src/nbody.rs:28-32); one Engine per process, guarded by one mutex (the reference holds
+// its mutex for the whole of every nb_* call).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/nbody_b200.h"
+#include "nb_common.cuh"
+
+namespace nb {
+
+constexpr int kMaxRanks = 8;
+constexpr int kShardAlign = 1024;  // shard length granularity (bodies); j tiles divide it
+constexpr int kFlagSlots = 64;
+
+// Symmetric arena: the part of a rank's state that peers may read over NVLink.  One cudaMalloc, one
+// IPC handle.  All offsets are identical on every rank.  L = shard_len (bodies per rank, padded).
+//   x[2][L]  y[2][L]   ping-pong position buffers (step s reads buffer s&1, writes (s+1)&1)
+//   m[L]               masses (constant during stepping; 0 for padding slots)
+//   vx[L] vy[L]        velocities of the local shard (read by peers only for nb_get_particles)
+//   flags[kFlagSlots]  uint32 step counters written by peers (flags[r] = steps rank r has completed)
+struct ArenaLayout {
+    size_t L = 0;
+    size_t off_x[2] = {0, 0}, off_y[2] = {0, 0}, off_m = 0, off_vx = 0, off_vy = 0, off_flags = 0, bytes = 0;
+    void set(size_t shard_len) {
+        L = shard_len;
+        size_t o = 0, f = shard_len * sizeof(float);
+        off_x[0] = o; o += f;
+        off_x[1] = o; o += f;
+        off_y[0] = o; o += f;
+        off_y[1] = o; o += f;
+        off_m = o; o += f;
+        off_vx = o; o += f;
+        off_vy = o; o += f;
+        off_flags = o; o += kFlagSlots * sizeof(uint32_t);
+        bytes = (o + 255) & ~size_t(255);
+    }
+};
+
+struct ArenaView {
+    char* base = nullptr;
+    float* x(const ArenaLayout& l, int b) const { return reinterpret_cast<float*>(base + l.off_x[b]); }
+    float* y(const ArenaLayout& l, int b) const { return reinterpret_cast<float*>(base + l.off_y[b]); }
+    float* m(const ArenaLayout& l) const { return reinterpret_cast<float*>(base + l.off_m); }
+    float* vx(const ArenaLayout& l) const { return reinterpret_cast<float*>(base + l.off_vx); }
+    float* vy(const ArenaLayout& l) const { return reinterpret_cast<float*>(base + l.off_vy); }
+    uint32_t* flags(const ArenaLayout& l) const { return reinterpret_cast<uint32_t*>(base + l.off_flags); }
+};
+
+// j-side source of one rank's shard for the all-pairs kernels.
+struct JSeg {
+    const float* x;
+    const float* y;
+    const float* m;
+};
+
+struct AllPairsArgs {
+    JSeg seg[kMaxRanks];       // seg[g] = positions/masses of global bodies [g*L, (g+1)*L)
+    int nseg;                  // world size
+    int seg_len;               // L
+    int n_total;               // real bodies in the global set (exact mode loops j < n_total)
+    const float* xi;           // local shard positions (current buffer)
+    const float* yi;
+    const float* mi;
+    int i_global_begin;        // global index of local body 0
+    int n_local;               // real local bodies
+    // fast path decomposition
+    int slice_len;             // j bodies per work item (multiple of the j tile)
+    int slices_per_seg;
+    float2* partial;           // [nseg*slices_per_seg][L] partial accelerations
+    // cross-rank ordering (P2P_DIRECT): wait until flags[g] >= wait_step before touching seg g != me
+    const uint32_t* flags;
+    uint32_t wait_step;
+    int my_rank;
+    // scheduling
+    unsigned int* work_counter;
+};
+
+struct Tuning {
+    int bodies_per_thread = 0;  // 0 = auto
+    int target_waves = 0;
+    int ctas_per_sm = 0;
+};
+
+struct Engine {
+    std::mutex mu;
+    bool inited = false;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int mode = NBX_MODE_FAST;
+    uint64_t seed = 0x5eed5eedULL;
+    Tuning tune;
+
+    // global set
+    int n = 0;
+    // sharding
+    int rank = 0, world = 1;
+    bool dist = false;
+    int transport = NBX_TRANSPORT_P2P_DIRECT;
+    int max_particles = 0;  // arena capacity in the dist case
+    ArenaLayout lay;
+    size_t arena_cap_bytes = 0;
+    ArenaView arena;                 // own
+    ArenaView peer[kMaxRanks];       // peer[rank] == arena
+    bool peers_mapped = false;
+    int cur = 0;                     // current position buffer
+    uint32_t step_count = 0;         // steps completed (also the cross-rank flag value)
+    // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies
+    float* mirror = nullptr;
+    size_t mirror_cap = 0;
+    // scratch
+    float2* partial = nullptr;
+    size_t partial_cap = 0;  // in float2
+    float2* force = nullptr; // exact-mode forces / accelerations [L]
+    size_t force_cap = 0;
+    unsigned int* work_counter = nullptr;
+    float* stage_host = nullptr;  // pinned staging for set/get
+    size_t stage_host_cap = 0;
+    float* stage_dev = nullptr;
+    size_t stage_dev_cap = 0;
+    void* l2_dummy = nullptr;
+
+    // counters / timing
+    nbx_counters ctr{};
+    bool bh_count = false;
+    bool phase_timing = false;
+    // ring of event pairs per phase: one slot per step since the last nbx_get_phase_ms, so the
+    // caller gets the AVERAGE device time per step of every phase over its timed region
+    static constexpr int kPhaseRing = 128;
+    cudaEvent_t ev[NBX_NUM_PHASES][kPhaseRing][2] = {};
+    int ev_count[NBX_NUM_PHASES] = {};
+    int ev_slot = 0;  // step index within the ring
+    float phase_ms[NBX_NUM_PHASES] = {};
+
+    // nccl (dlopen'ed), opaque here
+    void* nccl = nullptr;
+
+    // Barnes-Hut workspace, opaque (nb_bh.cu)
+    void* bh = nullptr;
+};
+
+Engine& engine();
+const char* last_error();
+int try_init(Engine& e, int device);
+void ensure_init(Engine& e);
+void step_brute_force(Engine& e, float dt);
+void accelerations_local(Engine& e);   // a_i of the local shard -> e.force
+void ensure_capacity(Engine& e, int n);   // (re)allocate arena/scratch for n global bodies
+int local_begin(const Engine& e);
+int local_count(const Engine& e);
+
+// phase timing helpers
+struct PhaseScope {
+    Engine& e;
+    int id;
+    PhaseScope(Engine& e_, int id_);
+    ~PhaseScope();
+};
+void collect_phase_times(Engine& e);
+
+// nb_state.cu
+void state_upload_aos(Engine& e, const float* aos5, int n);
+void state_download_aos(Engine& e, float* aos5, int n);
+void launch_integrate_fast(Engine& e, const float2* partial, int nslices, float dt, bool kill);
+void launch_integrate_exact(Engine& e, const float2* force, float dt, bool kill);
+void launch_fill_zero_f32(Engine& e, float* p, size_t n);
+void generate_random_disk(Engine& e, int n);
+void generate_stable_orbits(Engine& e, int n, float rmin, float rmax);
+
+// nb_allpairs.cu
+void allpairs_plan(Engine& e, AllPairsArgs& a);  // fills decomposition fields, grows scratch
+void launch_allpairs_fast(Engine& e, const AllPairsArgs& a);
+void launch_allpairs_exact(Engine& e, const AllPairsArgs& a, float2* force_out);
+void launch_accel_from_partial(Engine& e, const float2* partial, int nslices, float2* out);
+void launch_accel_from_force(Engine& e, const float2* force, float2* out);
+
+// nb_dist.cu
+void dist_fill_segments(Engine& e, AllPairsArgs& a);   // seg[] according to transport; may enqueue gather
+void dist_signal_step_done(Engine& e);                 // publish step_count to peers
+void dist_wait_all(Engine& e, uint32_t step);          // device-side wait for all peers
+void dist_gather_mirror(Engine& e, int buf);           // mirror <- all shards (own kernel or NCCL)
+void dist_barrier_host(Engine& e);
+void dist_shutdown(Engine& e);
+int dist_init(Engine& e, int rank, int world, int max_particles);
+int dist_export(Engine& e, void* out64);
+int dist_import(Engine& e, const void* all, int world);
+int dist_nccl_unique_id(void* out128);
+int dist_nccl_init(Engine& e, const void* id128);
+
+// nb_bh.cu
+void bh_step(Engine& e, float theta, float dt);
+void bh_accelerations(Engine& e, float theta, float2* out);
+void bh_shutdown(Engine& e);
+
+// nb_draw.cu
+void draw_to_host(Engine& e, int w, int h, uint32_t* fb);
+
+}  // namespace nb

@@ -1,0 +1,85 @@
+"""torch.distributed plumbing for the index-sharded particle set (one process per GPU).
+
+torch.distributed is used ONLY to wire the processes together (exchange the 64-byte CUDA IPC handles of
+the symmetric arenas, broadcast the NCCL unique id, barrier / max-reduce timings).  The data path of a
+step never goes through it: positions move GPU-to-GPU inside the library's own kernels (bulk-TMA loads
+from peer HBM over NVLink) or, for the baseline transport, the library's own ncclAllGather.
+
+The shard arithmetic here mirrors nb_dist.cu::dist_init / nb_engine.cu::local_begin so that it can be
+tested on CPU (gloo) without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+SHARD_ALIGN = 1024  # nb_engine.h kShardAlign
+MAX_RANKS = 8  # nb_engine.h kMaxRanks
+
+
+@dataclass(frozen=True)
+class ShardLayout:
+    """Rank g owns global bodies [g*L, min((g+1)*L, n)); slots beyond n are zero-mass padding."""
+
+    world: int
+    shard_len: int  # L
+
+    @staticmethod
+    def for_capacity(max_particles: int, world: int) -> "ShardLayout":
+        if not (1 <= world <= MAX_RANKS):
+            raise ValueError(f"world must be 1..{MAX_RANKS}")
+        if max_particles < 1:
+            raise ValueError("max_particles must be >= 1")
+        per = (max_particles + world - 1) // world
+        L = (per + SHARD_ALIGN - 1) // SHARD_ALIGN * SHARD_ALIGN
+        return ShardLayout(world, L)
+
+    def local_range(self, rank: int, n: int) -> tuple[int, int]:
+        b = min(rank * self.shard_len, n)
+        c = max(0, min(self.shard_len, n - rank * self.shard_len))
+        return b, c
+
+    def owner(self, i: int) -> int:
+        return i // self.shard_len
+
+    def segment_order(self, rank: int) -> list[int]:
+        """Order in which a rank's all-pairs kernel consumes j segments: its own first (needs no
+        cross-rank wait), then ring order -- nb_allpairs.cu `g = (my_rank + q) % nseg`."""
+        return [(rank + q) % self.world for q in range(self.world)]
+
+
+def all_gather_bytes(payload: bytes, group=None) -> list[bytes]:
+    import torch.distributed as dist
+
+    out: list = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, payload, group=group)
+    return out
+
+
+def broadcast_bytes(payload: bytes | None, src: int = 0, group=None) -> bytes:
+    import torch.distributed as dist
+
+    box = [payload]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]
+
+
+def wire(lib, max_particles: int, transport: int = 0, group=None) -> ShardLayout:
+    """Collective: allocate + exchange the symmetric arenas of all ranks and (optionally) set up NCCL."""
+    import torch.distributed as dist
+
+    from .binding import TRANSPORT_NCCL
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lib.dist_init(rank, world, max_particles)
+    handles = all_gather_bytes(lib.dist_export(), group)
+    lib.dist_import(b"".join(handles), world)
+    if transport == TRANSPORT_NCCL:
+        uid = lib.dist_nccl_unique_id() if rank == 0 else None
+        uid = broadcast_bytes(uid, 0, group)
+        lib.dist_nccl_init(uid)
+    lib.dist_set_transport(transport)
+    dist.barrier(group)
+    lay = ShardLayout.for_capacity(max_particles, world)
+    b, c = lib.dist_local_range()
+    assert (b, c) == lay.local_range(rank, lib.num_particles()), "host/library shard arithmetic disagree"
+    return lay

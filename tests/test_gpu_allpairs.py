@@ -1,0 +1,224 @@
+"""GPU: parity of the all-pairs path (nb_step_brute_force) through the C ABI against the oracle.
+
+Ladder: EXACT mode == oracle bit for bit; FAST mode within the stated FP32 tolerance of both;
+both against the f64 evaluation of the same pair law.  Tolerances (BASELINE.json north_star):
+positions max|dp|/extent <= 1e-4 after the stated number of steps, velocities <= 1e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from rust_exp_b200 import binding, ic
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nbody_golden.npz"))
+f32 = np.float32
+POS_TOL, VEL_TOL = 1e-4, 1e-3
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def rel_err(a, b, cols):
+    ext = np.abs(b[:, cols]).max()
+    return float(np.abs(a[:, cols].astype(np.float64) - b[:, cols]).max() / ext)
+
+
+def run_gpu(lib, s, dt, steps):
+    lib.set_particles(s)
+    for _ in range(steps):
+        lib.step_brute_force(dt)
+    return lib.get_particles()
+
+
+def run_ora(oracle, s, dt, steps):
+    oracle.set_particles(s)
+    for _ in range(steps):
+        oracle.step_brute_force(dt)
+    return oracle.get_particles()
+
+
+# ---------------------------------------------------------------- EXACT mode: bit parity ----------
+def test_exact_kat1_bit_patterns(fresh):
+    fresh.set_mode(binding.MODE_EXACT)
+    out = run_gpu(fresh, GOLD["kat1_in"], 0.01, 1)
+    assert np.array_equal(bits(out), bits(GOLD["kat1_out"]))
+    p = bits(out)
+    assert p[0, 0] == 0x3951B1B8 and p[0, 2] == 0x3CA3D2D8 and p[1, 0] == 0x3F7FF972 and p[1, 2] == 0xBC23D2D8
+
+
+@pytest.mark.parametrize("key,src", [("brute_disk_dt001_k5", "disk"), ("brute_orbits_dt001_k5", "orbits")])
+def test_exact_golden_fixtures(fresh, key, src):
+    fresh.set_mode(binding.MODE_EXACT)
+    assert np.array_equal(bits(run_gpu(fresh, GOLD[src], 0.01, 5)), bits(GOLD[key]))
+
+
+@pytest.mark.parametrize("n,steps,gen", [
+    (1, 3, "disk"), (2, 3, "disk"), (127, 5, "disk"), (1024, 100, "orbits"), (1025, 10, "disk"),
+    (4097, 5, "disk"), (8192, 20, "plummer")])
+def test_exact_matches_oracle_bitwise(fresh, oracle, n, steps, gen):
+    s = {"disk": ic.random_disk, "orbits": ic.stable_orbits, "plummer": ic.plummer_2d}[gen](n) if gen != "orbits" \
+        else ic.stable_orbits(n, 0.5, 30.0, seed=1)
+    fresh.set_mode(binding.MODE_EXACT)
+    g = run_gpu(fresh, s, 0.01, steps)
+    r = run_ora(oracle, s, 0.01, steps)
+    assert np.array_equal(bits(g), bits(r))
+
+
+def test_exact_theta_zero_is_brute_force_no_kill(fresh, oracle):
+    s = ic.random_disk(300, seed=4)
+    s[0, 0] = 80.0
+    s[0, 2] = 1.0
+    fresh.set_mode(binding.MODE_EXACT)
+    fresh.set_particles(s)
+    fresh.step_barnes_hut(0.0, 0.01, 4)  # KAT-3: theta == 0 -> brute force, nthreads ignored, no kill
+    a = fresh.get_particles()
+    b = run_ora(oracle, s, 0.01, 1)
+    assert np.array_equal(bits(a), bits(b)) and a[0, 2] != 0
+
+
+def test_exact_c2_size_65536_one_step(fresh, oracle):
+    """configs[1] size: 65,536-body Plummer, bit parity of one full step (oracle rows on all cores)."""
+    n = 65536
+    s = ic.plummer_2d(n, seed=2)
+    fresh.set_mode(binding.MODE_EXACT)
+    g = run_gpu(fresh, s, 0.01, 1)
+    oracle.set_particles(s)
+    f = oracle.brute_forces_rows(0, n, nthreads=os.cpu_count() or 1)
+    dt = f32(0.01)
+    r = s.copy()
+    r[:, 2] = r[:, 2] + (dt * f[:, 0]) / r[:, 4]
+    r[:, 3] = r[:, 3] + (dt * f[:, 1]) / r[:, 4]
+    r[:, 0] = r[:, 0] + dt * r[:, 2]
+    r[:, 1] = r[:, 1] + dt * r[:, 3]
+    assert np.array_equal(bits(g), bits(r))
+
+
+# ---------------------------------------------------------------- FAST mode: tolerance -------------
+@pytest.mark.parametrize("n,steps,gen,seed", [
+    (1024, 100, "orbits", 1),      # configs[0]: 1,024-body disk galaxy, K=100
+    (1024, 100, "disk", 1),
+    (8192, 100, "plummer", 2),     # K=100 at 8,192
+    (1000, 20, "disk", 9),         # ragged (not a multiple of any tile)
+    (513, 20, "disk", 10)])
+def test_fast_within_tolerance_of_oracle(fresh, oracle, n, steps, gen, seed):
+    s = ic.stable_orbits(n, 0.5, 30.0, seed=seed) if gen == "orbits" else \
+        (ic.random_disk(n, seed=seed) if gen == "disk" else ic.plummer_2d(n, seed=seed))
+    g = run_gpu(fresh, s, 0.01, steps)
+    r = run_ora(oracle, s, 0.01, steps)
+    assert rel_err(g, r, [0, 1]) <= POS_TOL
+    assert rel_err(g, r, [2, 3]) <= VEL_TOL
+    assert np.array_equal(g[:, 4], s[:, 4])
+
+
+@pytest.mark.parametrize("bpt", [1, 2, 4])
+def test_fast_all_register_tilings_agree(fresh, oracle, bpt):
+    s = ic.random_disk(3000, seed=12)
+    fresh.tune(bpt, 0, 0)
+    g = run_gpu(fresh, s, 0.01, 10)
+    r = run_ora(oracle, s, 0.01, 10)
+    assert rel_err(g, r, [0, 1]) <= POS_TOL and rel_err(g, r, [2, 3]) <= VEL_TOL
+
+
+def test_fast_accelerations_vs_f64_at_65536(fresh, oracle):
+    """configs[1] size.  The fast kernel must be at least as close to the f64 pair law as the reference's
+    own sequential-f32 semantics are."""
+    n = 65536
+    s = ic.plummer_2d(n, seed=2)
+    fresh.set_particles(s)
+    a_fast = fresh.accelerations().astype(np.float64)
+    fresh.set_mode(binding.MODE_EXACT)
+    a_exact = fresh.accelerations().astype(np.float64)
+    rows = np.random.default_rng(0).choice(n, 2048, replace=False).astype(np.int32)
+    oracle.set_particles(s)
+    a64 = oracle.accel_f64_rows(rows)
+    scale = np.abs(a64).max()
+    e_fast = np.abs(a_fast[rows] - a64).max() / scale
+    e_exact = np.abs(a_exact[rows] - a64).max() / scale
+    assert e_fast <= 2e-5
+    assert e_fast <= 4 * e_exact + 1e-6
+
+
+def test_fast_1m_sampled_rows_and_conservation(fresh, oracle):
+    """configs[2] size (1,048,576 bodies): sampled-row parity against f64 and the
+    size-independent property sum_i m_i a_i = 0 (antisymmetry of the pair law, KAT-2)."""
+    n = 1 << 20
+    s = ic.plummer_2d(n, seed=3)
+    fresh.set_particles(s)
+    a = fresh.accelerations().astype(np.float64)
+    rows = np.random.default_rng(1).choice(n, 256, replace=False).astype(np.int32)
+    oracle.set_particles(s)
+    a64 = oracle.accel_f64_rows(rows)
+    assert np.abs(a[rows] - a64).max() / np.abs(a64).max() <= 2e-5
+    m = s[:, 4:5].astype(np.float64)
+    assert np.abs((m * a).sum(0)).max() <= 1e-6 * np.abs(m * a).sum()
+
+
+def test_fast_is_deterministic_and_independent_of_decomposition(fresh):
+    s = ic.random_disk(20000, seed=13)
+    a = run_gpu(fresh, s, 0.01, 3)
+    b = run_gpu(fresh, s, 0.01, 3)
+    assert np.array_equal(bits(a), bits(b))
+    fresh.tune(0, 3, 1)  # different slice count / grid -> different summation grouping, same tolerance
+    c = run_gpu(fresh, s, 0.01, 3)
+    assert rel_err(c, a, [0, 1]) <= 1e-6
+
+
+# ---------------------------------------------------------------- edge cases -----------------------
+def test_empty_and_single_body(fresh):
+    fresh.set_particles(np.zeros((0, 5), dtype=f32))
+    fresh.step_brute_force(0.01)
+    assert fresh.num_particles() == 0 and fresh.get_particles().shape == (0, 5)
+    one = np.array([[1.0, 2.0, 0.5, -0.5, 3.0]], dtype=f32)
+    for mode in (binding.MODE_FAST, binding.MODE_EXACT):
+        fresh.set_mode(mode)
+        q = run_gpu(fresh, one, 0.1, 1)
+        assert q[0, 0] == f32(1.0) + f32(0.1) * f32(0.5) and q[0, 2] == f32(0.5) and q[0, 4] == 3.0
+
+
+def test_coincident_bodies_are_finite(fresh, oracle):
+    s = ic.random_disk(64, seed=14)
+    s[1, :2] = s[0, :2]  # identical positions: softened, finite, zero mutual force
+    for mode in (binding.MODE_FAST, binding.MODE_EXACT):
+        fresh.set_mode(mode)
+        q = run_gpu(fresh, s, 0.01, 2)
+        assert np.isfinite(q).all()
+    fresh.set_mode(binding.MODE_EXACT)
+    assert np.array_equal(bits(run_gpu(fresh, s, 0.01, 2)), bits(run_ora(oracle, s, 0.01, 2)))
+
+
+def test_set_get_roundtrip_and_resize(fresh):
+    for n in (5000, 100, 70000):
+        s = ic.random_disk(n, seed=n)
+        fresh.set_particles(s)
+        assert fresh.num_particles() == n
+        assert np.array_equal(bits(fresh.get_particles()), bits(s))
+
+
+def test_generators_distribution_level(fresh):
+    fresh.seed(123)
+    fresh.stable_orbits(10000, 0.5, 30.0)
+    a = fresh.get_particles()
+    assert a.shape == (10000, 5) and tuple(a[0]) == (0, 0, 0, 0, 1000.0)
+    r = np.hypot(a[1:, 0], a[1:, 1])
+    assert r.min() >= 0.5 - 1e-3 and r.max() <= 30.0 + 1e-3 and abs(r.mean() - 15.25) < 0.3
+    assert np.allclose(np.hypot(a[1:, 2], a[1:, 3]), np.sqrt(1000.0), rtol=1e-4)
+    fresh.random_disk(20000)
+    d = fresh.get_particles()
+    rr = np.hypot(d[:, 0], d[:, 1])
+    assert rr.max() <= 23.0 + 1e-3 and abs((rr ** 2).mean() - 23.0 ** 2 / 2) < 8.0  # uniform in area
+    assert d[:, 4].min() >= 0.1 and d[:, 4].max() <= 1.5 and np.abs(d[:, 2:4]).max() <= 3.5
+    fresh.seed(123)
+    fresh.random_disk(20000)
+    assert np.array_equal(bits(fresh.get_particles()), bits(d))  # seeded => reproducible
+
+
+def test_counters_report_kernel_launches(fresh):
+    fresh.set_particles(ic.random_disk(2048, seed=1))
+    fresh.reset_counters()
+    fresh.step_brute_force(0.01)
+    fresh.synchronize()
+    c = fresh.counters()
+    assert c["kernel_launches"] == 2 and c["allpairs_pairs"] == 2048 * 2047 and c["steps"] == 1

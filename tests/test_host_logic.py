@@ -1,0 +1,111 @@
+"""CPU: host-side logic -- the experiment plug-in mirror, the IC generators, the shard arithmetic."""
+import numpy as np
+import pytest
+
+from rust_exp_b200 import ic
+from rust_exp_b200.dist import ShardLayout
+from rust_exp_b200.experiment import RustNBodyExperiment
+
+
+class FakeLib:
+    """Records the C calls the plug-in makes (the boundary contract of hs-src/RustNBodyExperiment.hs)."""
+
+    def __init__(self):
+        self.calls = []
+        self.n = 0
+
+    def stable_orbits(self, n, a, b):
+        self.calls.append(("nb_stable_orbits", n, a, b)); self.n = n
+
+    def random_disk(self, n):
+        self.calls.append(("nb_random_disk", n)); self.n = n
+
+    def step_barnes_hut(self, theta, dt, nt):
+        self.calls.append(("nb_step_barnes_hut", theta, dt, nt))
+
+    def synchronize(self):
+        pass
+
+    def draw(self, w, h, fb):
+        self.calls.append(("nb_draw", w, h))
+
+    def num_particles(self):
+        return self.n
+
+
+def test_experiment_defaults_and_call_order():
+    L = FakeLib()
+    e = RustNBodyExperiment(L)
+    assert L.calls == [("nb_stable_orbits", 10000, 0.5, 30.0)]  # hs-src/RustNBodyExperiment.hs:42
+    assert (e.time_step, e.theta, e.num_threads, e.num_steps) == (0.01, 0.85, 1, 0)
+    fb = np.zeros((48, 64), dtype=np.uint32)
+    e.draw(fb)
+    # theta FIRST (rs-src/nbody.rs:187), step before draw (hs-src/RustNBodyExperiment.hs:55-60)
+    assert L.calls[1] == ("nb_step_barnes_hut", 0.85, 0.01, 1)
+    assert L.calls[2] == ("nb_draw", 64, 48)
+    assert e.num_steps == 1 and len(e.times) == 1
+
+
+def test_experiment_keys_and_clamps():
+    L = FakeLib()
+    e = RustNBodyExperiment(L)
+    e.key("W"); assert L.calls[-1] == ("nb_random_disk", 10000)
+    e.key("E"); assert L.calls[-1] == ("nb_stable_orbits", 5, 5.0, 40.0)
+    e.key("Q"); assert L.calls[-1] == ("nb_stable_orbits", 10000, 0.5, 30.0)
+    e.key("X"); assert e.time_step == 0.02
+    e.key("X", shift=True); e.key("X", shift=True); assert e.time_step == 0.005
+    for _ in range(10):
+        e.key("A")
+    assert e.theta == 0.95  # clamp, hs-src/RustNBodyExperiment.hs:90-93
+    for _ in range(40):
+        e.key("A", shift=True)
+    assert e.theta == 0.0  # theta can reach exactly 0 -> brute-force path (rs-src/nbody.rs:197)
+    for _ in range(40):
+        e.key("P")
+    assert e.num_threads == 16
+    for _ in range(40):
+        e.key("P", shift=True)
+    assert e.num_threads == 1
+
+
+def test_experiment_status_string_format():
+    L = FakeLib()
+    e = RustNBodyExperiment(L)
+    s = e.status_string()
+    assert s.startswith("0 Steps, 1.0SPS/1000.00ms | 10K Bodies\n")
+    assert "Time Step [X][x]: 0.0100 | Theta [A][a]: 0.85 | Threads [P][p]: 1" in s
+    e.key("E")
+    assert "| 5 Bodies" in e.status_string()
+    e.times.extend([0.01, 0.03, 0.02])
+    assert "50.0SPS/20.00ms" in e.status_string()  # median, hs-src/RustNBodyExperiment.hs:65
+
+
+def test_ic_generators_match_reference_distributions():
+    a = ic.stable_orbits(1024, 0.5, 30.0, seed=1)
+    assert a.dtype == np.float32 and a.shape == (1024, 5)
+    assert tuple(a[0]) == (0, 0, 0, 0, 1000.0)
+    r = np.hypot(a[1:, 0], a[1:, 1]); v = np.hypot(a[1:, 2], a[1:, 3])
+    assert r.min() >= 0.5 - 1e-4 and r.max() <= 30.0 + 1e-4
+    assert np.allclose(v, np.sqrt(1000.0), rtol=1e-5)
+    assert np.allclose(a[1:, 0] * a[1:, 2] + a[1:, 1] * a[1:, 3], 0, atol=1e-2)  # v perpendicular to r
+    d = ic.random_disk(4096, seed=2)
+    assert np.hypot(d[:, 0], d[:, 1]).max() <= 23.0 + 1e-4
+    assert d[:, 4].min() >= 0.1 and d[:, 4].max() < 1.5 and np.abs(d[:, 2:4]).max() <= 3.5
+    p = ic.plummer_2d(4096, seed=3)
+    assert np.abs(p[:, :2]).max() < 55.0  # fits the kill box
+    assert np.array_equal(ic.plummer_2d(4096, seed=3), p)  # reproducible
+
+
+def test_shard_layout_matches_library_arithmetic():
+    lay = ShardLayout.for_capacity(1 << 20, 8)
+    assert lay.shard_len == 131072
+    assert [lay.local_range(r, 1 << 20) for r in (0, 7)] == [(0, 131072), (917504, 131072)]
+    lay = ShardLayout.for_capacity(1000, 2)  # ragged: L = 1024, rank 1 owns nothing
+    assert lay.shard_len == 1024
+    assert lay.local_range(0, 1000) == (0, 1000) and lay.local_range(1, 1000) == (1000, 0)
+    lay = ShardLayout.for_capacity(5000, 4)  # L = 2048
+    assert [lay.local_range(r, 5000) for r in range(4)] == [(0, 2048), (2048, 2048), (4096, 904), (5000, 0)]
+    assert sum(c for _, c in (lay.local_range(r, 5000) for r in range(4))) == 5000
+    assert lay.segment_order(2) == [2, 3, 0, 1]
+    with pytest.raises(ValueError):
+        ShardLayout.for_capacity(10, 9)
