@@ -241,7 +241,11 @@ def main():
 
     lib = pkg.load()
     lib.init(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: handle 0 would mean "library's own stream" to nbx_set_stream,
+    # and torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     lib.set_stream(stream.cuda_stream)  # torch CUDA events then bracket the library's launches
     lib.tune(args.bodies_per_thread, args.waves, args.ctas_per_sm)
     n = w["n"]

@@ -125,6 +125,8 @@ int32_t nbx_get_phase_ms(float *out8);
 /* Accelerations only (no state update) of the current set with the current mode, a_i = F_i / m_i in
  * the reference's units, written to a HOST array of 2*n floats.  Used by sampled parity checks. */
 int32_t nbx_accelerations(float *axy_out, int32_t n);
+/* Same through the Barnes-Hut tree (build + traversal with opening angle theta, no state update). */
+int32_t nbx_bh_accelerations(float theta, float *axy_out, int32_t n);
 
 /* ---- multi-GPU (one process per GPU; particles shard by index) -------------
  * Wiring is done by the host framework's process group (torch.distributed in this repo):

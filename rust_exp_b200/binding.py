@@ -43,6 +43,7 @@ SYMBOLS = {
     "nbx_phase_timing": (i32, [i32]),
     "nbx_get_phase_ms": (i32, [vp]),
     "nbx_accelerations": (i32, [vp, i32]),
+    "nbx_bh_accelerations": (i32, [f32, vp, i32]),
     "nbx_dist_init": (i32, [i32, i32, i32]),
     "nbx_dist_handle_bytes": (i32, []),
     "nbx_dist_export": (i32, [vp]),
@@ -183,6 +184,12 @@ class NBodyLib:
         n = self.num_particles() if n is None else n
         out = np.zeros((n, 2), dtype=np.float32)
         self._chk(self.L.nbx_accelerations(out.ctypes.data, n), "nbx_accelerations")
+        return out
+
+    def bh_accelerations(self, theta: float, n: int | None = None) -> np.ndarray:
+        n = self.num_particles() if n is None else n
+        out = np.zeros((n, 2), dtype=np.float32)
+        self._chk(self.L.nbx_bh_accelerations(theta, out.ctypes.data, n), "nbx_bh_accelerations")
         return out
 
     # ---- multi-GPU -------------------------------------------------------------------------------

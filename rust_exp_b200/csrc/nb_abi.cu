@@ -246,6 +246,22 @@ int32_t nbx_accelerations(float* axy_out, int32_t n) {
     return 0;
 }
 
+int32_t nbx_bh_accelerations(float theta, float* axy_out, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    if (e.n == 0 || n <= 0) return 0;
+    bh_accelerations(e, theta, e.force);
+    const int b = local_begin(e);
+    int c = local_count(e);
+    if (b + c > n) c = n - b;
+    if (c > 0)
+        NB_CUDA(cudaMemcpyAsync(axy_out + 2 * static_cast<size_t>(b), e.force, sizeof(float2) * c, cudaMemcpyDeviceToHost,
+                                e.stream));
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    return 0;
+}
+
 int32_t nbx_dist_init(int32_t rank, int32_t world, int32_t max_particles) {
     NB_LOCK();
     Engine& e = engine();

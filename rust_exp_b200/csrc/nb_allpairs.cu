@@ -68,8 +68,8 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flags, int g, uint32_t
     __threadfence_system();
 }
 
-template <int I>
-__global__ void __launch_bounds__(kThreads, (I <= 2) ? 3 : 2) allpairs_fast_kernel(const AllPairsArgs a) {
+template <int I, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const AllPairsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
 
@@ -222,8 +222,12 @@ static int pick_bodies_per_thread(const Engine& e) {
     return 2;
 }
 static int pick_ctas_per_sm(const Engine& e, int I) {
-    if (e.tune.ctas_per_sm > 0) return e.tune.ctas_per_sm;
-    return I <= 2 ? 3 : 2;
+    int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I <= 2 ? 3 : 2);
+    // clamp to the instantiated variants
+    if (I == 1) c = c < 3 ? 3 : (c > 5 ? 5 : c);
+    else if (I == 4) c = c < 1 ? 1 : (c > 2 ? 2 : c);
+    else c = c < 2 ? 2 : (c > 4 ? 4 : c);
+    return c;
 }
 
 void allpairs_plan(Engine& e, AllPairsArgs& a) {
@@ -259,11 +263,11 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     a.partial = e.partial;
 }
 
-template <int I>
+template <int I, int MINB>
 static void launch_fast_t(Engine& e, const AllPairsArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(allpairs_fast_kernel<I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NB_CUDA(cudaFuncSetAttribute(allpairs_fast_kernel<I, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(FastSmem))));
         attr_set = true;
     }
@@ -271,18 +275,28 @@ static void launch_fast_t(Engine& e, const AllPairsArgs& a) {
     const int n_itiles = (a.n_local + TI - 1) / TI;
     const int n_items = n_itiles * a.nseg * a.slices_per_seg;
     if (n_items == 0) return;
-    int grid = e.num_sms * pick_ctas_per_sm(e, I);
+    int grid = e.num_sms * MINB;
     if (grid > n_items) grid = n_items;
-    allpairs_fast_kernel<I><<<grid, kThreads, sizeof(FastSmem), e.stream>>>(a);
+    allpairs_fast_kernel<I, MINB><<<grid, kThreads, sizeof(FastSmem), e.stream>>>(a);
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
 }
 
 void launch_allpairs_fast(Engine& e, const AllPairsArgs& a) {
-    switch (pick_bodies_per_thread(e)) {
-        case 1: launch_fast_t<1>(e, a); break;
-        case 4: launch_fast_t<4>(e, a); break;
-        default: launch_fast_t<2>(e, a); break;
+    const int I = pick_bodies_per_thread(e);
+    const int C = pick_ctas_per_sm(e, I);
+    // (bodies per thread, resident CTAs per SM) variants; the register budget follows from MINB
+    if (I == 1) {
+        if (C <= 3) launch_fast_t<1, 3>(e, a);
+        else if (C == 4) launch_fast_t<1, 4>(e, a);
+        else launch_fast_t<1, 5>(e, a);
+    } else if (I == 4) {
+        if (C <= 1) launch_fast_t<4, 1>(e, a);
+        else launch_fast_t<4, 2>(e, a);
+    } else {
+        if (C <= 2) launch_fast_t<2, 2>(e, a);
+        else if (C == 3) launch_fast_t<2, 3>(e, a);
+        else launch_fast_t<2, 4>(e, a);
     }
     e.ctr.allpairs_pairs += static_cast<uint64_t>(a.n_local) * static_cast<uint64_t>(a.n_total > 0 ? a.n_total - 1 : 0);
 }

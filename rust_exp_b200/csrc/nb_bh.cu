@@ -1,7 +1,675 @@
-// nb_bh.cu -- Barnes-Hut step (rs-src/nbody.rs:186-480).  Placeholder until the device tree lands.
+// nb_bh.cu -- Barnes-Hut step on the device (rs-src/nbody.rs:186-480).
+//
+// Pipeline of one step (all on the library stream, no host round trip):
+//   aabb      tight, non-square bounding box (rs-src/nbody.rs:388-398); exact (min/max do not round)
+//   keys      per body, the quadrant path of the reference's own f32 midpoint recursion
+//             cx=(x1+x2)*0.5 (rs-src/nbody.rs:289-290,322-331) -> 2 bits per level, child order
+//             UL=0 UR=1 LL=2 LR=3 (:295-300).  Cell boundaries therefore match the reference bit for bit.
+//   sort      CUB radix sort of (key, index); stable, so equal keys keep particle-index order
+//   scan      f64 prefix sums of m, m*x, m*y over the sorted bodies: any node's mass and centre of mass
+//             is a difference of two prefix entries, so the build is purely top-down
+//   build     level-synchronous: a node with range [first, first+count) in sorted order splits into
+//             four children located by binary search on the 2 key bits of its level.  Splitting stops at
+//             count<=1, at a too-close pair (|dx|,|dy| < EPS: the reference's merge rule, :249-260), or at
+//             the last key level (cells there are smaller than EPS, so their bodies would merge too).
+//   traverse  FAST: one warp per 32 Morton-consecutive bodies, shared-memory node stack; the warp walks
+//             the union of its lanes' DFS paths, but every lane applies the reference's own per-body
+//             opening test and is masked off inside subtrees it has accepted -- so each body evaluates
+//             exactly the interaction list the reference would (:333-377), summed in DFS order.
+//             EXACT: one thread per body, explicit frame stack reproducing the nested summation order.
+//   integrate Euler + velocity kill (:453-471).
+//
+// EXACT mode builds the tree with a literal single-thread restatement of Node::insert (:226-284) so that
+// insertion-order effects (running-mean COM rounding, merges) are reproduced bit for bit; it is the
+// semantics pin for the tree, not a throughput path.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "nb_engine.h"
+
 namespace nb {
-void bh_step(Engine&, float, float) { fatal("nb_step_barnes_hut: device tree not built into this library yet", __FILE__, __LINE__); }
-void bh_accelerations(Engine&, float, float2*) { fatal("bh_accelerations: not built yet", __FILE__, __LINE__); }
-void bh_shutdown(Engine&) {}
+
+constexpr int kLevels = 24;            // key levels (2 bits each); root cell / 2^24 < EPS for extents < 1677
+constexpr int kKeyBits = 2 * kLevels;
+constexpr int kNone = 0x7fffffff;
+constexpr int kStackPerWarp = 4 * kLevels + 8;
+constexpr int kTravWarps = 8;
+
+struct BhStatus {
+    int node_count;
+    int overflow;
+    int ticket;
+    int depth_error;          // exact build: recursion depth > 50 (the reference panics)
+    int lvl_begin[kLevels + 3];
+    int aabb_enc[4];          // ordered-int encodings of x1,y1 (min) and x2,y2 (max)
+    int n_mine;
+    int pad;
+    unsigned long long interactions;
+    unsigned long long visited;
+};
+
+struct BhWork {
+    int cap_n = 0;
+    unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+    int *idx = nullptr, *idx_sorted = nullptr, *mine = nullptr;
+    float *sx = nullptr, *sy = nullptr, *sm = nullptr;
+    double *w3 = nullptr;      // [3][n+1] weights then prefix sums (m, m*x, m*y)
+    double *p3 = nullptr;
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    int cap_nodes = 0;
+    float4* ndata = nullptr;   // com.x, com.y, mass, width (s = x2-x1; < 0 marks a leaf)
+    float4* nbounds = nullptr; // x1,y1,x2,y2
+    int* nchild = nullptr;     // first of 4 children, -1 for a leaf
+    int2* nrange = nullptr;    // first, count (sorted order)
+    BhStatus* status = nullptr;
+    BhStatus* status_host = nullptr;
+    float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
+    int cap_acc = 0;
+    bool warned = false;
+};
+
+static BhWork& work(Engine& e) {
+    if (!e.bh) e.bh = new BhWork();
+    return *static_cast<BhWork*>(e.bh);
+}
+
+__device__ __forceinline__ int f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// ---- aabb -----------------------------------------------------------------------------------------
+__global__ void bh_reset_kernel(BhStatus* st) {
+    if (threadIdx.x == 0) {
+        st->node_count = 1;
+        st->overflow = 0;
+        st->ticket = 0;
+        st->depth_error = 0;
+        for (int l = 0; l < kLevels + 3; l++) st->lvl_begin[l] = (l == 0) ? 0 : 1;
+        st->aabb_enc[0] = st->aabb_enc[1] = f2ord(3.40282347e+38f);
+        st->aabb_enc[2] = st->aabb_enc[3] = f2ord(-3.40282347e+38f);
+        st->interactions = 0;
+        st->visited = 0;
+    }
+}
+
+__global__ void bh_aabb_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, BhStatus* st) {
+    int mnx = f2ord(3.40282347e+38f), mny = mnx, mxx = f2ord(-3.40282347e+38f), mxy = mxx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int ex = f2ord(x[i]), ey = f2ord(y[i]);
+        mnx = min(mnx, ex); mxx = max(mxx, ex);
+        mny = min(mny, ey); mxy = max(mxy, ey);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&st->aabb_enc[0], mnx);
+        atomicMin(&st->aabb_enc[1], mny);
+        atomicMax(&st->aabb_enc[2], mxx);
+        atomicMax(&st->aabb_enc[3], mxy);
+    }
+}
+
+// ---- keys: the reference's midpoint recursion, kLevels deep ------------------------------------------
+__global__ void bh_keys_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, const BhStatus* st,
+                               unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x1 = ord2f(st->aabb_enc[0]), y1 = ord2f(st->aabb_enc[1]);
+    float x2 = ord2f(st->aabb_enc[2]), y2 = ord2f(st->aabb_enc[3]);
+    const float px = x[i], py = y[i];
+    unsigned long long key = 0;
+#pragma unroll 4
+    for (int l = 0; l < kLevels; l++) {
+        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f);  // rs-src/nbody.rs:289-290 / :324-325
+        const float cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+        const bool lower = py < cy, left = px < cx;           // rs-src/nbody.rs:326-330
+        const unsigned q = (lower ? 2u : 0u) | (left ? 0u : 1u);
+        key = (key << 2) | q;
+        // child bounds, rs-src/nbody.rs:295-300
+        if (left) x2 = cx; else x1 = cx;
+        if (lower) y2 = cy; else y1 = cy;
+    }
+    keys[i] = key;
+    idx[i] = i;
+}
+
+__global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                        const float* __restrict__ m, const int* __restrict__ idx_sorted, int n,
+                                        float* __restrict__ sx, float* __restrict__ sy, float* __restrict__ sm,
+                                        double* __restrict__ w3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    double wm = 0.0, wx = 0.0, wy = 0.0;
+    if (i < n) {
+        const int j = idx_sorted[i];
+        const float xx = x[j], yy = y[j], mm = m[j];
+        sx[i] = xx; sy[i] = yy; sm[i] = mm;
+        wm = mm; wx = static_cast<double>(mm) * xx; wy = static_cast<double>(mm) * yy;
+    }
+    const size_t stride = static_cast<size_t>(n) + 1;
+    w3[i] = wm; w3[stride + i] = wx; w3[2 * stride + i] = wy;
+}
+
+// ---- build: one level per launch ----------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_quadrant(const unsigned long long* __restrict__ keys, int lo, int hi,
+                                                    int shift, unsigned q) {
+    // first position in [lo,hi) whose 2 key bits at `shift` are >= q (keys are sorted)
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (((keys[mid] >> shift) & 3ull) < q) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// rs-src/nbody.rs:303-320 with the reference's rounding (used for merged leaves)
+__device__ __forceinline__ void add_mass_ref(float& px, float& py, float& m, float x, float y, float mm) {
+    if (m == 0.0f) {
+        px = x; py = y; m = mm;
+    } else {
+        const float inv = __fdiv_rn(1.0f, __fadd_rn(m, mm));
+        px = __fmul_rn(__fadd_rn(__fmul_rn(px, m), __fmul_rn(x, mm)), inv);
+        py = __fmul_rn(__fadd_rn(__fmul_rn(py, m), __fmul_rn(y, mm)), inv);
+        m = __fadd_rn(m, mm);
+    }
+}
+
+__global__ void bh_build_level_kernel(int level, int n, int cap_nodes, const unsigned long long* __restrict__ keys,
+                                      const float* __restrict__ sx, const float* __restrict__ sy,
+                                      const float* __restrict__ sm, const double* __restrict__ p3,
+                                      float4* __restrict__ ndata, float4* __restrict__ nbounds, int* __restrict__ nchild,
+                                      int2* __restrict__ nrange, BhStatus* st) {
+    const int begin = st->lvl_begin[level], end = st->lvl_begin[level + 1];
+    const size_t stride = static_cast<size_t>(n) + 1;
+    for (int node = begin + blockIdx.x * blockDim.x + threadIdx.x; node < end; node += gridDim.x * blockDim.x) {
+        int2 r;
+        float4 b;
+        if (level == 0) {
+            r = make_int2(0, n);
+            b = make_float4(ord2f(st->aabb_enc[0]), ord2f(st->aabb_enc[1]), ord2f(st->aabb_enc[2]), ord2f(st->aabb_enc[3]));
+            nbounds[0] = b;
+            nrange[0] = r;
+        } else {
+            r = nrange[node];
+            b = nbounds[node];
+        }
+        const int first = r.x, count = r.y;
+        float cxm = 0.f, cym = 0.f, mass = 0.f;
+        bool leaf = true;
+        if (count == 1) {
+            cxm = sx[first]; cym = sy[first]; mass = sm[first];  // exact copy (self-skip relies on it, :305-311)
+        } else if (count >= 2) {
+            // merge rule (rs-src/nbody.rs:249-260): bodies closer than EPS in both axes share a leaf.
+            // Stable sort => equal-key bodies are in index order; the fold below is the reference's add_mass.
+            bool close = (level >= kLevels);
+            if (!close && count <= 32) {
+                float lx = sx[first], hx = lx, ly = sy[first], hy = ly;
+                for (int k = 1; k < count; k++) {
+                    lx = fminf(lx, sx[first + k]); hx = fmaxf(hx, sx[first + k]);
+                    ly = fminf(ly, sy[first + k]); hy = fmaxf(hy, sy[first + k]);
+                }
+                close = (hx - lx) < kEps && (hy - ly) < kEps;
+            }
+            if (!close && st->node_count + 4 > cap_nodes) { close = true; st->overflow = 1; }
+            if (close) {
+                for (int k = 0; k < count; k++) add_mass_ref(cxm, cym, mass, sx[first + k], sy[first + k], sm[first + k]);
+            } else {
+                leaf = false;
+            }
+        }
+        int child = -1;
+        if (!leaf) {
+            const int c0 = atomicAdd(&st->node_count, 4);
+            if (c0 + 4 > cap_nodes) {  // lost the race for the last slots: degrade to a merged leaf
+                st->overflow = 1;
+                for (int k = 0; k < count; k++) add_mass_ref(cxm, cym, mass, sx[first + k], sy[first + k], sm[first + k]);
+                leaf = true;
+            } else {
+                child = c0;
+                // centre of mass from the f64 prefix sums
+                const double M = p3[first + count] - p3[first];
+                const double MX = p3[stride + first + count] - p3[stride + first];
+                const double MY = p3[2 * stride + first + count] - p3[2 * stride + first];
+                mass = static_cast<float>(M);
+                cxm = static_cast<float>(MX / M);
+                cym = static_cast<float>(MY / M);
+                // children: rs-src/nbody.rs:286-301
+                const float cx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f);
+                const float cy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
+                const int shift = 2 * (kLevels - 1 - level);
+                const int e1 = lower_bound_quadrant(keys, first, first + count, shift, 1u);
+                const int e2 = lower_bound_quadrant(keys, e1, first + count, shift, 2u);
+                const int e3 = lower_bound_quadrant(keys, e2, first + count, shift, 3u);
+                nbounds[c0 + 0] = make_float4(b.x, cy, cx, b.w);   // UL
+                nbounds[c0 + 1] = make_float4(cx, cy, b.z, b.w);   // UR
+                nbounds[c0 + 2] = make_float4(b.x, b.y, cx, cy);   // LL
+                nbounds[c0 + 3] = make_float4(cx, b.y, b.z, cy);   // LR
+                nrange[c0 + 0] = make_int2(first, e1 - first);
+                nrange[c0 + 1] = make_int2(e1, e2 - e1);
+                nrange[c0 + 2] = make_int2(e2, e3 - e2);
+                nrange[c0 + 3] = make_int2(e3, first + count - e3);
+            }
+        }
+        nchild[node] = child;
+        ndata[node] = make_float4(cxm, cym, mass, leaf ? -1.0f : __fsub_rn(b.z, b.x));  // s = x2 - x1 (:341)
+    }
+    // last block to finish publishes the end of the next level
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(&st->ticket, 1);
+        is_last = (t == static_cast<int>(gridDim.x) - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        const int nc = min(*reinterpret_cast<volatile int*>(&st->node_count), cap_nodes);
+        st->lvl_begin[level + 2] = nc;
+        st->ticket = 0;
+        __threadfence();
+    }
+}
+
+// ---- EXACT build: literal serial restatement of rs-src/nbody.rs:226-320, one thread ---------------------
+__global__ void bh_build_serial_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                       const float* __restrict__ m, int n, int cap_nodes, float4* ndata,
+                                       float4* nbounds, int* nchild, BhStatus* st) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int node_count = 1;
+    nbounds[0] = make_float4(ord2f(st->aabb_enc[0]), ord2f(st->aabb_enc[1]), ord2f(st->aabb_enc[2]), ord2f(st->aabb_enc[3]));
+    ndata[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    nchild[0] = -1;
+    for (int i = 0; i < n; i++) {
+        const float px = x[i], py = y[i], pm = m[i];
+        int node = 0;
+        unsigned depth = 0;
+        while (true) {
+            if (depth > 50) { st->depth_error = 1; break; }       // :230-232 (the reference panics)
+            float4 d = ndata[node];
+            const int ch = nchild[node];
+            if (ch >= 0) {                                          // :234-247 interior
+                add_mass_ref(d.x, d.y, d.z, px, py, pm);
+                ndata[node] = d;
+                const float4 b = nbounds[node];
+                const float cx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f);
+                const float cy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
+                const int q = (py < cy) ? ((px < cx) ? 2 : 3) : ((px < cx) ? 0 : 1);
+                node = ch + q;
+                depth++;
+                continue;
+            }
+            const bool too_close = fabsf(__fsub_rn(d.x, px)) < kEps && fabsf(__fsub_rn(d.y, py)) < kEps;  // :249
+            if (d.z == 0.0f || too_close) {                         // :250-260
+                add_mass_ref(d.x, d.y, d.z, px, py, pm);
+                ndata[node] = d;
+                break;
+            }
+            // :261-282 split: clear, create children, re-insert the original, then keep inserting
+            if (node_count + 4 > cap_nodes) { st->overflow = 1; break; }
+            const float4 b = nbounds[node];
+            const float cx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f);
+            const float cy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
+            const int c0 = node_count;
+            node_count += 4;
+            nbounds[c0 + 0] = make_float4(b.x, cy, cx, b.w);
+            nbounds[c0 + 1] = make_float4(cx, cy, b.z, b.w);
+            nbounds[c0 + 2] = make_float4(b.x, b.y, cx, cy);
+            nbounds[c0 + 3] = make_float4(cx, b.y, b.z, cy);
+            for (int k = 0; k < 4; k++) { ndata[c0 + k] = make_float4(0.f, 0.f, 0.f, 0.f); nchild[c0 + k] = -1; }
+            nchild[node] = c0;
+            // self.insert(original, depth+1): interior now, mass 0 -> exact copy, then the empty child takes it
+            if (depth + 1 > 50 || depth + 2 > 50) { st->depth_error = 1; break; }
+            const int qo = (d.y < cy) ? ((d.x < cx) ? 2 : 3) : ((d.x < cx) ? 0 : 1);
+            ndata[c0 + qo] = make_float4(d.x, d.y, d.z, 0.f);
+            ndata[node] = make_float4(d.x, d.y, d.z, 0.f);
+            depth++;                                                // self.insert(px,py,m, depth+1) on this node
+        }
+        if (st->depth_error || st->overflow) break;
+    }
+    st->node_count = node_count;
+}
+
+__global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const float4* __restrict__ nbounds,
+                                         const int* __restrict__ nchild, const BhStatus* st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st->node_count || i >= cap_nodes) return;
+    float4 d = ndata[i];
+    const float4 b = nbounds[i];
+    d.w = nchild[i] >= 0 ? __fsub_rn(b.z, b.x) : -1.0f;
+    ndata[i] = d;
+}
+
+// ---- traversal, FAST ---------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
+    const float4* __restrict__ ndata, const int* __restrict__ nchild, const float* __restrict__ sx,
+    const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
+    int i_begin, float theta2, float2* __restrict__ acc, BhStatus* st) {
+    __shared__ unsigned stk[kTravWarps][kStackPerWarp];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kTravWarps + warp;
+    const int li = w * 32 + lane;
+    if (w * 32 >= n_list) return;
+    const bool live = li < n_list;
+    const int pos = live ? (mine ? mine[li] : li) : 0;  // position in sorted order
+    const float px = sx[pos], py = sy[pos];
+    float ax = 0.f, ay = 0.f;
+    int blocked = live ? kNone : -1;
+    unsigned* s = stk[warp];
+    int sp = 1;
+    if (lane == 0) s[0] = 0u;
+    __syncwarp();
+    unsigned long long n_int = 0, n_vis = 0;
+    while (sp > 0) {
+        --sp;
+        const unsigned e = s[sp];
+        __syncwarp();
+        const int node = static_cast<int>(e & 0x3ffffffu), d = static_cast<int>(e >> 26);
+        if (d <= blocked) blocked = kNone;   // the DFS has left the subtree this lane accepted
+        const float4 nd = __ldg(&ndata[node]);
+        const bool active = (blocked == kNone);
+        const float dx = nd.x - px, dy = nd.y - py;
+        const float d2 = fmaf(dy, dy, dx * dx);
+        if (COUNT) n_vis += active ? 1 : 0;
+        if (nd.w < 0.f) {
+            // leaf (rs-src/nbody.rs:363-374): skip own entry (bitwise position match) and empty nodes
+            if (active && nd.z != 0.f && !(nd.x == px && nd.y == py)) {
+                const float sc = nd.z * rcp_approx(d2 + kEps);
+                ax = fmaf(sc, dx, ax); ay = fmaf(sc, dy, ay);
+                if (COUNT) n_int++;
+            }
+        } else {
+            // interior (:339-361): accept iff s/d < theta  <=>  s^2 < theta^2 d^2
+            const bool accept = (nd.w * nd.w) < theta2 * d2;
+            if (active && accept) {
+                const float sc = nd.z * rcp_approx(d2 + kEps);
+                ax = fmaf(sc, dx, ax); ay = fmaf(sc, dy, ay);
+                blocked = d;
+                if (COUNT) n_int++;
+            }
+            if (__any_sync(0xffffffffu, active && !accept)) {
+                const int c = __ldg(&nchild[node]);
+                if (lane < 4) s[sp + 3 - lane] = static_cast<unsigned>(c + lane) | (static_cast<unsigned>(d + 1) << 26);
+                sp += 4;
+                __syncwarp();
+            }
+        }
+    }
+    if (live) acc[idx_sorted[pos] - i_begin] = make_float2(ax, ay);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            n_int += __shfl_xor_sync(0xffffffffu, n_int, o);
+            n_vis += __shfl_xor_sync(0xffffffffu, n_vis, o);
+        }
+        if (lane == 0) { atomicAdd(&st->interactions, n_int); atomicAdd(&st->visited, n_vis); }
+    }
+}
+
+// ---- traversal, EXACT: rs-src/nbody.rs:333-377 with its nested summation order ------------------------------
+struct Frame { int node; int next; float fx, fy; };
+
+__device__ __forceinline__ void force_ref(float px1, float py1, float m1, float px2, float py2, float m2, float& fx, float& fy) {
+    const float dx = __fsub_rn(px2, px1), dy = __fsub_rn(py2, py1);              // rs-src/nbody.rs:174-175
+    const float dist_sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const float f = __fdiv_rn(__fmul_rn(m1, m2), __fadd_rn(dist_sq, kEps));      // :180
+    fx = __fmul_rn(f, dx); fy = __fmul_rn(f, dy);
+}
+
+__global__ void bh_traverse_exact_kernel(const float4* __restrict__ ndata, const int* __restrict__ nchild,
+                                         const float* __restrict__ x, const float* __restrict__ y,
+                                         const float* __restrict__ m, int i_begin, int n_local, float theta,
+                                         float2* __restrict__ force_out) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= n_local) return;
+    const float px = x[i_begin + il], py = y[i_begin + il], pm = m[i_begin + il];
+    Frame st[64];
+    int sp = 0;
+    st[0] = Frame{0, -1, 0.f, 0.f};
+    float rx = 0.f, ry = 0.f;  // value returned by the frame that just finished
+    while (sp >= 0) {
+        Frame& f = st[sp];
+        if (f.next < 0) {
+            // first visit: evaluate the node
+            const float4 nd = ndata[f.node];
+            if (nd.w >= 0.f) {  // interior
+                const float dx = __fsub_rn(nd.x, px), dy = __fsub_rn(nd.y, py);
+                const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));  // :344
+                if (__fdiv_rn(nd.w, d) < theta) {                                           // :345
+                    force_ref(px, py, pm, nd.x, nd.y, nd.z, rx, ry);
+                    sp--;
+                } else {
+                    f.next = 0; f.fx = 0.f; f.fy = 0.f;
+                    const int c = nchild[f.node];
+                    st[sp + 1] = Frame{c, -1, 0.f, 0.f};
+                    f.next = 1;
+                    sp++;
+                    continue;
+                }
+            } else {  // leaf :363-374
+                if ((nd.x == px && nd.y == py) || nd.z == 0.0f) { rx = 0.f; ry = 0.f; }
+                else force_ref(px, py, pm, nd.x, nd.y, nd.z, rx, ry);
+                sp--;
+            }
+        } else {
+            // a child returned (rx,ry): fx += fx_add (:358-359)
+            f.fx = __fadd_rn(f.fx, rx);
+            f.fy = __fadd_rn(f.fy, ry);
+            if (f.next < 4) {
+                const int c = nchild[f.node] + f.next;
+                f.next++;
+                st[sp + 1] = Frame{c, -1, 0.f, 0.f};
+                sp++;
+                continue;
+            }
+            rx = f.fx; ry = f.fy;
+            sp--;
+        }
+        if (sp < 0) break;
+    }
+    force_out[il] = make_float2(rx, ry);
+}
+
+// mine[] = sorted positions whose body index lies in [b, b+c)
+struct InRange {
+    const int* idx_sorted;
+    int b, e;
+    __device__ bool operator()(int pos) const { const int i = idx_sorted[pos]; return i >= b && i < e; }
+};
+using Iota = thrust::counting_iterator<int>;
+
+// ---- host orchestration ----------------------------------------------------------------------------------------
+static void ensure_work(Engine& e, BhWork& w, int n) {
+    if (n > w.cap_n) {
+        NB_CUDA(cudaStreamSynchronize(e.stream));
+        auto fr = [](void* p) { if (p) cudaFree(p); };
+        fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
+        fr(w.w3); fr(w.p3); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp);
+        const size_t N = static_cast<size_t>(n);
+        NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
+        NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
+        NB_CUDA(cudaMalloc(&w.sx, N * 4)); NB_CUDA(cudaMalloc(&w.sy, N * 4)); NB_CUDA(cudaMalloc(&w.sm, N * 4));
+        NB_CUDA(cudaMalloc(&w.w3, 3 * (N + 1) * 8)); NB_CUDA(cudaMalloc(&w.p3, 3 * (N + 1) * 8));
+        w.cap_nodes = static_cast<int>(std::min<size_t>(8 * N + 4096, 0x3fffff0));
+        NB_CUDA(cudaMalloc(&w.ndata, sizeof(float4) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.nbounds, sizeof(float4) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.nchild, sizeof(int) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.nrange, sizeof(int2) * w.cap_nodes));
+        size_t b1 = 0, b2 = 0, b3 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, e.stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, w.w3, w.p3, 3 * (n + 1), e.stream);
+        cub::DeviceSelect::If(nullptr, b3, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.idx_sorted, 0, n}, e.stream);
+        w.cub_bytes = std::max(b1, std::max(b2, b3)) + 256;
+        NB_CUDA(cudaMalloc(&w.cub_tmp, w.cub_bytes));
+        w.cap_n = n;
+    }
+}
+
+static void ensure_status(BhWork& w) {
+    if (!w.status) {
+        NB_CUDA(cudaMalloc(&w.status, sizeof(BhStatus)));
+        NB_CUDA(cudaMallocHost(&w.status_host, sizeof(BhStatus)));
+        memset(w.status_host, 0, sizeof(BhStatus));
+    }
+}
+
+// positions of ALL bodies for the tree: the arena on one GPU, the gathered mirror when sharded
+struct GlobalPos { const float *x, *y, *m; };
+static GlobalPos global_positions(Engine& e) {
+    if (!e.dist || e.world == 1) return GlobalPos{e.arena.x(e.lay, e.cur), e.arena.y(e.lay, e.cur), e.arena.m(e.lay)};
+    PhaseScope ps(e, 7);
+    dist_gather_mirror(e, e.cur);
+    const size_t GL = static_cast<size_t>(e.world) * e.lay.L;
+    return GlobalPos{e.mirror, e.mirror + GL, e.mirror + 2 * GL};
+}
+
+// builds the tree over all e.n bodies and leaves per-local-body acceleration (FAST) / force (EXACT) in w.acc
+static void bh_forces(Engine& e, float theta) {
+    BhWork& w = work(e);
+    ensure_status(w);
+    const int n = e.n;
+    ensure_work(e, w, n);
+    const int nl = local_count(e), ib = local_begin(e);
+    if (nl > w.cap_acc) {
+        if (w.acc) NB_CUDA(cudaFree(w.acc));
+        NB_CUDA(cudaMalloc(&w.acc, sizeof(float2) * static_cast<size_t>(e.lay.L)));
+        w.cap_acc = static_cast<int>(e.lay.L);
+    }
+    // sharded: slot index == body index only while every shard but the last is full (L-aligned shards)
+    const GlobalPos gp = global_positions(e);
+    cudaStream_t s = e.stream;
+    const int T = 256, G = (n + T - 1) / T;
+    {
+        PhaseScope ps(e, 2);
+        bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
+        bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
+        e.ctr.kernel_launches += 2;
+    }
+    if (e.mode == NBX_MODE_EXACT) {
+        {
+            PhaseScope ps(e, 5);
+            bh_build_serial_kernel<<<1, 32, 0, s>>>(gp.x, gp.y, gp.m, n, w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
+            bh_finalize_exact_kernel<<<(w.cap_nodes + T - 1) / T, T, 0, s>>>(w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
+            e.ctr.kernel_launches += 2;
+        }
+        PhaseScope ps(e, 0);
+        if (nl > 0) {
+            bh_traverse_exact_kernel<<<(nl + 127) / 128, 128, 0, s>>>(w.ndata, w.nchild, gp.x, gp.y, gp.m, ib, nl, theta, w.acc);
+            e.ctr.kernel_launches++;
+        }
+    } else {
+        {
+            PhaseScope ps(e, 3);
+            bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
+            e.ctr.kernel_launches++;
+        }
+        {
+            PhaseScope ps(e, 4);
+            size_t tb = w.cub_bytes;
+            cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, s);
+        }
+        {
+            PhaseScope ps(e, 6);
+            bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
+            e.ctr.kernel_launches++;
+            size_t tb = w.cub_bytes;
+            // one exclusive scan over the three concatenated [n+1] segments; segment k's sums are taken as
+            // differences inside the segment, so the carried-in offset cancels
+            cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.w3, w.p3, 3 * (n + 1), s);
+        }
+        {
+            PhaseScope ps(e, 5);
+            const int grid = e.num_sms * 2;
+            for (int l = 0; l <= kLevels; l++) {
+                bh_build_level_kernel<<<grid, T, 0, s>>>(l, n, w.cap_nodes, w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.ndata,
+                                                        w.nbounds, w.nchild, w.nrange, w.status);
+            }
+            e.ctr.kernel_launches += kLevels + 1;
+        }
+        const int* mine = nullptr;
+        int n_list = n;
+        if (e.dist && e.world > 1) {
+            size_t tb = w.cub_bytes;
+            cub::DeviceSelect::If(w.cub_tmp, tb, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.idx_sorted, ib, ib + nl}, s);
+            mine = w.mine;
+            n_list = nl;
+        }
+        PhaseScope ps(e, 0);
+        if (n_list > 0) {
+            const int blocks = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
+            if (e.bh_count)
+                bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, s>>>(w.ndata, w.nchild, w.sx, w.sy, w.idx_sorted, mine,
+                                                                                n_list, ib, theta * theta, w.acc, w.status);
+            else
+                bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, s>>>(w.ndata, w.nchild, w.sx, w.sy, w.idx_sorted, mine,
+                                                                                 n_list, ib, theta * theta, w.acc, w.status);
+            e.ctr.kernel_launches++;
+        }
+    }
+    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
+}
+
+static void check_status(Engine& e, BhWork& w) {
+    // deferred: looks at the status of the step that has just been enqueued (one stream sync per BH step)
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    const BhStatus& h = *w.status_host;
+    if (h.depth_error) fatal("Node::insert() - recursion depth > 50 (the reference panics here, rs-src/nbody.rs:230-232)", __FILE__, __LINE__);
+    if (h.overflow && !w.warned) {
+        fprintf(stderr, "nbody_b200: warning: quadtree node pool exhausted (%d nodes); deepest cells were merged\n", w.cap_nodes);
+        w.warned = true;
+    }
+    e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
+    e.ctr.bh_interactions += h.interactions;
+    e.ctr.bh_nodes_visited += h.visited;
+}
+
+void bh_step(Engine& e, float theta, float dt) {
+    if (e.n == 0) return;
+    BhWork& w = work(e);
+    bh_forces(e, theta);
+    {
+        PhaseScope ps(e, 1);
+        if (e.mode == NBX_MODE_EXACT) launch_integrate_exact(e, w.acc, dt, true);
+        else launch_integrate_fast(e, w.acc, 1, dt, true);
+    }
+    e.step_count++;
+    dist_signal_step_done(e);
+    e.ctr.steps++;
+    if (e.phase_timing) e.ev_slot++;
+    check_status(e, w);
+}
+
+void bh_accelerations(Engine& e, float theta, float2* out) {
+    if (e.n == 0) return;
+    BhWork& w = work(e);
+    bh_forces(e, theta);
+    if (e.mode == NBX_MODE_EXACT) launch_accel_from_force(e, w.acc, out);
+    else launch_accel_from_partial(e, w.acc, 1, out);
+    e.step_count++;
+    dist_signal_step_done(e);
+    check_status(e, w);
+}
+
+void bh_shutdown(Engine& e) {
+    if (!e.bh) return;
+    BhWork& w = work(e);
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
+    fr(w.w3); fr(w.p3); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    if (w.status_host) cudaFreeHost(w.status_host);
+    delete &w;
+    e.bh = nullptr;
+}
+
 }  // namespace nb
