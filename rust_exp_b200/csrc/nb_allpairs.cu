@@ -222,7 +222,7 @@ static int pick_bodies_per_thread(const Engine& e) {
     return 2;
 }
 static int pick_ctas_per_sm(const Engine& e, int I) {
-    int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I <= 2 ? 3 : 2);
+    int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I == 1 ? 5 : (I == 2 ? 4 : 2));  // measured best, profiles/
     // clamp to the instantiated variants
     if (I == 1) c = c < 3 ? 3 : (c > 5 ? 5 : c);
     else if (I == 4) c = c < 1 ? 1 : (c > 2 ? 2 : c);
@@ -243,7 +243,7 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     const int TI = kComputeThreads * I;
     const int n_itiles = (a.n_local + TI - 1) / TI;
     const int R = e.num_sms * pick_ctas_per_sm(e, I);
-    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : 16;
+    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : 64;
     int want_total = (W * R + n_itiles - 1) / (n_itiles > 0 ? n_itiles : 1);
     int per_seg = (want_total + a.nseg - 1) / a.nseg;
     const int max_per_seg = L / kTJ;

@@ -1,0 +1,137 @@
+"""Multi-GPU parity + transport comparison, one rank per GPU.  Launch:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+Checks (rank 0 prints one JSON line per check, exit code != 0 on failure):
+  * EXACT mode, sharded over N GPUs == single-process oracle, bit for bit (brute force and Barnes-Hut)
+  * FAST mode: the three transports (P2P_DIRECT, P2P_GATHER, NCCL) give bitwise identical results
+  * FAST sharded vs oracle within the 1e-4 tolerance; ragged sizes; nb_draw / nb_get on every rank
+  * per-transport step time at a larger size
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402  (this is a test tool)
+import rust_exp_b200 as pkg  # noqa: E402
+from rust_exp_b200 import binding, ic  # noqa: E402
+from rust_exp_b200 import dist as nbdist  # noqa: E402
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    lib = pkg.load()
+    lib.init(lr)
+    big = int(os.environ.get("NB_DIST_BIG", 262144))
+    nbdist.wire(lib, max(big, 70000), binding.TRANSPORT_NCCL)  # NCCL comm + IPC arenas; transports switch below
+    o = oracle.get()
+    ok = True
+
+    def report(name, passed, **kw):
+        nonlocal ok
+        ok = ok and bool(passed)
+        if rank == 0:
+            print(json.dumps({"check": name, "pass": bool(passed), **kw}), flush=True)
+
+    # ---- EXACT sharded == oracle ----------------------------------------------------------------
+    for n, steps in ((3000, 5), (4096, 3), (1, 2)):
+        s = ic.random_disk(n, seed=41)
+        lib.set_mode(binding.MODE_EXACT)
+        for tr in (binding.TRANSPORT_P2P_DIRECT, binding.TRANSPORT_P2P_GATHER, binding.TRANSPORT_NCCL):
+            lib.dist_set_transport(tr)
+            lib.set_particles(s)
+            for _ in range(steps):
+                lib.step_brute_force(0.01)
+            g = lib.get_particles()
+            o.set_particles(s)
+            for _ in range(steps):
+                o.step_brute_force(0.01)
+            report(f"exact_brute_n{n}_transport{tr}", np.array_equal(bits(g), bits(o.get_particles())))
+        lib.dist_set_transport(binding.TRANSPORT_P2P_GATHER)
+        lib.set_particles(s)
+        for _ in range(steps):
+            lib.step_barnes_hut(0.5, 0.01, 1)
+        g = lib.get_particles()
+        o.set_particles(s)
+        for _ in range(steps):
+            o.step_barnes_hut(0.5, 0.01, 2)
+        report(f"exact_bh_n{n}", np.array_equal(bits(g), bits(o.get_particles())))
+    lib.set_mode(binding.MODE_FAST)
+
+    # ---- FAST: transports agree bitwise; within tolerance of the oracle ----------------------------
+    n, steps = 20000, 10
+    s = ic.plummer_2d(n, seed=42)
+    outs = {}
+    for tr in (binding.TRANSPORT_P2P_DIRECT, binding.TRANSPORT_P2P_GATHER, binding.TRANSPORT_NCCL):
+        lib.dist_set_transport(tr)
+        lib.set_particles(s)
+        for _ in range(steps):
+            lib.step_brute_force(0.01)
+        outs[tr] = lib.get_particles()
+    report("fast_transports_bitwise_equal", np.array_equal(bits(outs[0]), bits(outs[1])) and np.array_equal(bits(outs[0]), bits(outs[2])))
+    o.set_particles(s)
+    for _ in range(steps):
+        o.step_brute_force(0.01)
+    r = o.get_particles()
+    err = float(np.abs(outs[0][:, :2].astype(np.float64) - r[:, :2]).max() / np.abs(r[:, :2]).max())
+    report("fast_brute_vs_oracle", err <= 1e-4, rel_pos_err=err)
+    # every rank must hold the same gathered state
+    allg = [None] * world
+    dist.all_gather_object(allg, bits(outs[0]).tobytes())
+    report("get_particles_identical_on_all_ranks", all(a == allg[0] for a in allg))
+
+    lib.dist_set_transport(binding.TRANSPORT_P2P_GATHER)
+    lib.set_particles(s)
+    for _ in range(5):
+        lib.step_barnes_hut(0.5, 0.01, 1)
+    g = lib.get_particles()
+    o.set_particles(s)
+    for _ in range(5):
+        o.step_barnes_hut(0.5, 0.01, 2)
+    r = o.get_particles()
+    err = float(np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max() / np.abs(r[:, :2]).max())
+    report("fast_bh_vs_oracle", err <= 1e-4, rel_pos_err=err)
+    fb = lib.draw(128, 96)
+    o.set_particles(g)
+    report("draw_sharded", np.array_equal(fb, o.draw(128, 96)))
+
+    # ---- timing per transport -----------------------------------------------------------------------
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    lib.set_stream(st.cuda_stream)
+    sb = ic.plummer_2d(big, seed=43)
+    for tr, name in ((0, "p2p_direct"), (1, "p2p_gather"), (2, "nccl")):
+        lib.dist_set_transport(tr)
+        lib.set_particles(sb)
+        for _ in range(3):
+            lib.step_brute_force(0.01)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        reps = 10
+        for _ in range(reps):
+            lib.step_brute_force(0.01)
+        e1.record(st)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        report(f"time_{name}", True, n=big, world=world, ms_per_step=float(t.item()),
+               pairs_per_s=big * (big - 1) / (float(t.item()) * 1e-3))
+    lib.set_stream(None)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
