@@ -23,7 +23,8 @@
 // insertion-order effects (running-mean COM rounding, merges) are reproduced bit for bit; it is the
 // semantics pin for the tree, not a throughput path.
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -60,6 +61,7 @@ struct BhWork {
     float *sx = nullptr, *sy = nullptr, *sm = nullptr;
     double *w3 = nullptr;      // [3][n+1] weights then prefix sums (m, m*x, m*y)
     double *p3 = nullptr;
+    double *tile_sums = nullptr;
     void* cub_tmp = nullptr;
     size_t cub_bytes = 0;
     int cap_nodes = 0;
@@ -160,6 +162,49 @@ __global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float
     }
     const size_t stride = static_cast<size_t>(n) + 1;
     w3[i] = wm; w3[stride + i] = wx; w3[2 * stride + i] = wy;
+}
+
+// ---- deterministic f64 exclusive scan ---------------------------------------------------------------------
+// cub::DeviceScan's decoupled look-back combines tile prefixes in a timing-dependent order, which for
+// floating point makes the low bits (and, rarely, a rounded COM and an opening test) vary from run to
+// run.  This reduce-then-scan has a fixed association: tile sums in a fixed tree, a single block scanning
+// the tile sums sequentially, then a fixed in-tile scan.  blockIdx.y selects one of the 3 arrays.
+constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const double* __restrict__ in, int len, size_t stride,
+                                                                      double* __restrict__ tile_sums, int ntiles) {
+    using BR = cub::BlockReduce<double, kScanThreads>;
+    __shared__ typename BR::TempStorage tmp;
+    const double* a = in + blockIdx.y * stride;
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) v += (base + k < len) ? a[base + k] : 0.0;
+    const double t = BR(tmp).Sum(v);
+    if (threadIdx.x == 0) tile_sums[blockIdx.y * ntiles + blockIdx.x] = t;
+}
+__global__ void scan_tile_offsets_kernel(double* tile_sums, int ntiles) {
+    // one thread per array: sequential, fixed order (ntiles <= a few thousand)
+    if (threadIdx.x == 0) {
+        double* t = tile_sums + blockIdx.x * ntiles;
+        double run = 0.0;
+        for (int i = 0; i < ntiles; i++) { const double v = t[i]; t[i] = run; run += v; }
+    }
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const double* __restrict__ in, double* __restrict__ out, int len,
+                                                                  size_t stride, const double* __restrict__ tile_offs, int ntiles) {
+    using BS = cub::BlockScan<double, kScanThreads>;
+    __shared__ typename BS::TempStorage tmp;
+    const double* a = in + blockIdx.y * stride;
+    double* o = out + blockIdx.y * stride;
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    double v[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) v[k] = (base + k < len) ? a[base + k] : 0.0;
+    BS(tmp).ExclusiveSum(v, v);
+    const double off = tile_offs[blockIdx.y * ntiles + blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) if (base + k < len) o[base + k] = off + v[k];
 }
 
 // ---- build: one level per launch ----------------------------------------------------------------------
@@ -494,7 +539,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         auto fr = [](void* p) { if (p) cudaFree(p); };
         fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-        fr(w.w3); fr(w.p3); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp);
+        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp);
         const size_t N = static_cast<size_t>(n);
         NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
         NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
@@ -505,9 +550,9 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaMalloc(&w.nbounds, sizeof(float4) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nchild, sizeof(int) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nrange, sizeof(int2) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
         size_t b1 = 0, b2 = 0, b3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, e.stream);
-        cub::DeviceScan::ExclusiveSum(nullptr, b2, w.w3, w.p3, 3 * (n + 1), e.stream);
         cub::DeviceSelect::If(nullptr, b3, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.idx_sorted, 0, n}, e.stream);
         w.cub_bytes = std::max(b1, std::max(b2, b3)) + 256;
         NB_CUDA(cudaMalloc(&w.cub_tmp, w.cub_bytes));
@@ -582,10 +627,12 @@ static void bh_forces(Engine& e, float theta) {
             PhaseScope ps(e, 6);
             bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
             e.ctr.kernel_launches++;
-            size_t tb = w.cub_bytes;
-            // one exclusive scan over the three concatenated [n+1] segments; segment k's sums are taken as
-            // differences inside the segment, so the carried-in offset cancels
-            cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.w3, w.p3, 3 * (n + 1), s);
+            const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
+            const size_t stride = static_cast<size_t>(n) + 1;
+            scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, len, stride, w.tile_sums, ntiles);
+            scan_tile_offsets_kernel<<<3, 32, 0, s>>>(w.tile_sums, ntiles);
+            scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, w.p3, len, stride, w.tile_sums, ntiles);
+            e.ctr.kernel_launches += 3;
         }
         {
             PhaseScope ps(e, 5);
@@ -666,7 +713,7 @@ void bh_shutdown(Engine& e) {
     BhWork& w = work(e);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-    fr(w.w3); fr(w.p3); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     delete &w;
     e.bh = nullptr;
