@@ -225,7 +225,7 @@ static int pick_ctas_per_sm(const Engine& e, int I) {
     int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I == 1 ? 5 : (I == 2 ? 4 : 2));  // measured best, profiles/
     // clamp to the instantiated variants
     if (I == 1) c = c < 3 ? 3 : (c > 5 ? 5 : c);
-    else if (I == 4) c = c < 1 ? 1 : (c > 2 ? 2 : c);
+    else if (I == 4) c = c < 1 ? 1 : (c > 3 ? 3 : c);
     else c = c < 2 ? 2 : (c > 4 ? 4 : c);
     return c;
 }
@@ -292,7 +292,8 @@ void launch_allpairs_fast(Engine& e, const AllPairsArgs& a) {
         else launch_fast_t<1, 5>(e, a);
     } else if (I == 4) {
         if (C <= 1) launch_fast_t<4, 1>(e, a);
-        else launch_fast_t<4, 2>(e, a);
+        else if (C == 2) launch_fast_t<4, 2>(e, a);
+        else launch_fast_t<4, 3>(e, a);
     } else {
         if (C <= 2) launch_fast_t<2, 2>(e, a);
         else if (C == 3) launch_fast_t<2, 3>(e, a);

@@ -25,6 +25,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/block/block_reduce.cuh>
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
@@ -68,7 +69,9 @@ struct BhWork {
     float4* ndata = nullptr;   // com.x, com.y, mass, width (s = x2-x1; < 0 marks a leaf)
     float4* nbounds = nullptr; // x1,y1,x2,y2
     int* nchild = nullptr;     // first of 4 children, -1 for a leaf
-    int2* nrange = nullptr;    // first, count (sorted order)
+    signed char *delta = nullptr, *dcap = nullptr;
+    unsigned char* close = nullptr;
+    int *count = nullptr, *base = nullptr;
     BhStatus* status = nullptr;
     BhStatus* status_host = nullptr;
     float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
@@ -207,7 +210,18 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const double* 
     for (int k = 0; k < kScanItems; k++) if (base + k < len) o[base + k] = off + v[k];
 }
 
-// ---- build: one level per launch ----------------------------------------------------------------------
+// ---- build: single pass over the sorted keys, no level synchronisation ---------------------------------
+//
+// delta(i) = number of quadtree levels on which sorted bodies i and i+1 share their cell (common key
+// prefix / 2 bits).  A cell with >= 2 bodies is an interior node unless all its bodies merge (reference rule
+// rs-src/nbody.rs:249-260: closer than EPS in both axes).  An interior node at level l whose first body is i
+// exists exactly for l in (dcap(i-1), dcap(i)], where dcap is delta capped (a) at kLevels-1 and (b), for
+// pairs inside a chain of mutually close bodies, below the first level at which the chain is alone in
+// its cell -- that cell becomes a merged leaf.  A prefix sum over count(i) = max(0, dcap(i)-dcap(i-1)) numbers
+// the interior nodes; node k owns the 4-slot child block [4+4k, 4+4k+4) (64-byte aligned float4 records),
+// and every node's record lives in its parent's block (the root in slot 0).  One thread per body then emits
+// the nodes that start at it: range end and child boundaries by binary search on the keys, mass/COM from the
+// f64 prefix sums, cell bounds by replaying the key bits through the reference's midpoint recursion.
 __device__ __forceinline__ int lower_bound_quadrant(const unsigned long long* __restrict__ keys, int lo, int hi,
                                                     int shift, unsigned q) {
     // first position in [lo,hi) whose 2 key bits at `shift` are >= q (keys are sorted)
@@ -230,99 +244,147 @@ __device__ __forceinline__ void add_mass_ref(float& px, float& py, float& m, flo
     }
 }
 
-__global__ void bh_build_level_kernel(int level, int n, int cap_nodes, const unsigned long long* __restrict__ keys,
-                                      const float* __restrict__ sx, const float* __restrict__ sy,
-                                      const float* __restrict__ sm, const double* __restrict__ p3,
-                                      float4* __restrict__ ndata, float4* __restrict__ nbounds, int* __restrict__ nchild,
-                                      int2* __restrict__ nrange, BhStatus* st) {
-    const int begin = st->lvl_begin[level], end = st->lvl_begin[level + 1];
-    const size_t stride = static_cast<size_t>(n) + 1;
-    for (int node = begin + blockIdx.x * blockDim.x + threadIdx.x; node < end; node += gridDim.x * blockDim.x) {
-        int2 r;
-        float4 b;
-        if (level == 0) {
-            r = make_int2(0, n);
-            b = make_float4(ord2f(st->aabb_enc[0]), ord2f(st->aabb_enc[1]), ord2f(st->aabb_enc[2]), ord2f(st->aabb_enc[3]));
-            nbounds[0] = b;
-            nrange[0] = r;
+// delta[i] for the pair (i, i+1), i in [0, n-1); bit 7 = "too close" flag.  delta[n-1] = sentinel -1.
+__global__ void bh_delta_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ sx,
+                                const float* __restrict__ sy, int n, signed char* __restrict__ delta,
+                                unsigned char* __restrict__ close) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == n - 1) { delta[i] = -1; close[i] = 0; return; }
+    const unsigned long long x = keys[i] ^ keys[i + 1];
+    const int d = x ? (__clzll(static_cast<long long>(x)) - (64 - kKeyBits)) >> 1 : kLevels;
+    delta[i] = static_cast<signed char>(d);
+    close[i] = (fabsf(sx[i] - sx[i + 1]) < kEps && fabsf(sy[i] - sy[i + 1]) < kEps) ? 1 : 0;
+}
+
+__global__ void bh_cap_kernel(const signed char* __restrict__ delta, const unsigned char* __restrict__ close, int n,
+                              signed char* __restrict__ dcap, int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto cap_of = [&](int j) -> int {   // capped delta of pair j (j in [-1, n-1])
+        if (j < 0 || j >= n - 1) return -1;
+        int d = min(static_cast<int>(delta[j]), kLevels - 1);
+        if (close[j]) {
+            int p = j, q = j + 1;            // chain of close pairs containing pair j: bodies p..q
+            for (int g = 0; g < 4096 && p > 0 && close[p - 1]; g++) p--;
+            for (int g = 0; g < 4096 && q < n - 1 && close[q]; g++) q++;
+            const int dl = p > 0 ? static_cast<int>(delta[p - 1]) : -1;
+            const int dr = q < n - 1 ? static_cast<int>(delta[q]) : -1;
+            d = min(d, max(dl, dr));         // l* - 1, l* = 1 + max(dl, dr)
+        }
+        return d;
+    };
+    const int c = cap_of(i), cl = cap_of(i - 1);
+    dcap[i] = static_cast<signed char>(c);
+    count[i] = max(0, c - cl);
+}
+
+struct BuildArgs {
+    const unsigned long long* keys;
+    const float *sx, *sy, *sm;
+    const double* p3;
+    const signed char* dcap;
+    const int* base;      // exclusive prefix of count[]
+    float4* ndata;
+    int* nchild;
+    int n, cap_interior;
+};
+
+__device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
+    // id of the interior node that starts at body `first` on `level`
+    const int dl = first > 0 ? static_cast<int>(a.dcap[first - 1]) : -1;
+    return a.base[first] + (level - dl - 1);
+}
+
+__global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const size_t stride = static_cast<size_t>(a.n) + 1;
+    const float rx1 = ord2f(st->aabb_enc[0]), ry1 = ord2f(st->aabb_enc[1]);
+    const float rx2 = ord2f(st->aabb_enc[2]), ry2 = ord2f(st->aabb_enc[3]);
+    const int dhi = a.dcap[i];
+    const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
+    if (i == 0) {
+        st->node_count = 1 + 4 * min(a.base[a.n - 1], a.cap_interior);   // count[n-1] == 0
+        if (a.base[a.n - 1] > a.cap_interior) st->overflow = 1;
+        if (dhi < 0) {
+            // no interior node at all: the root is a leaf (one body, or everything merges)
+            float cx = 0.f, cy = 0.f, mm = 0.f;
+            for (int k = 0; k < a.n; k++) add_mass_ref(cx, cy, mm, a.sx[k], a.sy[k], a.sm[k]);
+            a.ndata[0] = make_float4(cx, cy, mm, -1.0f);
+            a.nchild[0] = -1;
+        }
+    }
+    const unsigned long long key = a.keys[i];
+    for (int l = dlo + 1; l <= dhi; l++) {
+        const int id = a.base[i] + (l - dlo - 1);
+        if (id >= a.cap_interior) break;
+        // cell bounds at level l: replay the key bits through rs-src/nbody.rs:286-301
+        float x1 = rx1, y1 = ry1, x2 = rx2, y2 = ry2;
+        for (int t = 0; t < l; t++) {
+            const unsigned q = static_cast<unsigned>(key >> (2 * (kLevels - 1 - t))) & 3u;
+            const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+            if (q & 1u) x1 = cx; else x2 = cx;      // UR/LR: right half
+            if (q & 2u) y2 = cy; else y1 = cy;      // LL/LR: lower half
+        }
+        const int shift = 2 * (kLevels - 1 - l);
+        // end of this cell's range: first body whose level-l prefix differs
+        int end;
+        if (l == 0) {
+            end = a.n;
         } else {
-            r = nrange[node];
-            b = nbounds[node];
+            const unsigned long long pre = key >> (shift + 2);
+            int lo = i + 1, hi = a.n;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((a.keys[mid] >> (shift + 2)) == pre) lo = mid + 1; else hi = mid;
+            }
+            end = lo;
         }
-        const int first = r.x, count = r.y;
-        float cxm = 0.f, cym = 0.f, mass = 0.f;
-        bool leaf = true;
-        if (count == 1) {
-            cxm = sx[first]; cym = sy[first]; mass = sm[first];  // exact copy (self-skip relies on it, :305-311)
-        } else if (count >= 2) {
-            // merge rule (rs-src/nbody.rs:249-260): bodies closer than EPS in both axes share a leaf.
-            // Stable sort => equal-key bodies are in index order; the fold below is the reference's add_mass.
-            bool close = (level >= kLevels);
-            if (!close && count <= 32) {
-                float lx = sx[first], hx = lx, ly = sy[first], hy = ly;
-                for (int k = 1; k < count; k++) {
-                    lx = fminf(lx, sx[first + k]); hx = fmaxf(hx, sx[first + k]);
-                    ly = fminf(ly, sy[first + k]); hy = fmaxf(hy, sy[first + k]);
+        const int e1 = lower_bound_quadrant(a.keys, i, end, shift, 1u);
+        const int e2 = lower_bound_quadrant(a.keys, e1, end, shift, 2u);
+        const int e3 = lower_bound_quadrant(a.keys, e2, end, shift, 3u);
+        const int f[5] = {i, e1, e2, e3, end};
+        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+        const int blk = 4 + 4 * id;
+        if (l == 0) {   // the root's own record
+            const double M = a.p3[a.n] - a.p3[0];
+            a.ndata[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M),
+                                     static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M),
+                                     static_cast<float>(M), __fsub_rn(x2, x1));
+            a.nchild[0] = blk;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int first = f[q], cnt = f[q + 1] - f[q];
+            float4 rec = make_float4(0.f, 0.f, 0.f, -1.0f);
+            int child = -1;
+            if (cnt == 1) {
+                rec = make_float4(a.sx[first], a.sy[first], a.sm[first], -1.0f);   // exact copy (:305-311)
+            } else if (cnt >= 2) {
+                int cid = -1;
+                if (static_cast<int>(a.dcap[first]) >= l + 1) {
+                    cid = interior_id(a, first, l + 1);
+                    if (cid >= a.cap_interior) cid = -1;    // node pool exhausted: degrade to a merged leaf
                 }
-                close = (hx - lx) < kEps && (hy - ly) < kEps;
+                if (cid >= 0) {
+                    const double M = a.p3[first + cnt] - a.p3[first];
+                    const double MX = a.p3[stride + first + cnt] - a.p3[stride + first];
+                    const double MY = a.p3[2 * stride + first + cnt] - a.p3[2 * stride + first];
+                    // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
+                    const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
+                    rec = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
+                    child = 4 + 4 * cid;
+                } else {
+                    float bx = 0.f, by = 0.f, bm = 0.f;
+                    for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
+                    rec = make_float4(bx, by, bm, -1.0f);
+                }
             }
-            if (!close && st->node_count + 4 > cap_nodes) { close = true; st->overflow = 1; }
-            if (close) {
-                for (int k = 0; k < count; k++) add_mass_ref(cxm, cym, mass, sx[first + k], sy[first + k], sm[first + k]);
-            } else {
-                leaf = false;
-            }
+            a.ndata[blk + q] = rec;
+            a.nchild[blk + q] = child;
         }
-        int child = -1;
-        if (!leaf) {
-            const int c0 = atomicAdd(&st->node_count, 4);
-            if (c0 + 4 > cap_nodes) {  // lost the race for the last slots: degrade to a merged leaf
-                st->overflow = 1;
-                for (int k = 0; k < count; k++) add_mass_ref(cxm, cym, mass, sx[first + k], sy[first + k], sm[first + k]);
-                leaf = true;
-            } else {
-                child = c0;
-                // centre of mass from the f64 prefix sums
-                const double M = p3[first + count] - p3[first];
-                const double MX = p3[stride + first + count] - p3[stride + first];
-                const double MY = p3[2 * stride + first + count] - p3[2 * stride + first];
-                mass = static_cast<float>(M);
-                cxm = static_cast<float>(MX / M);
-                cym = static_cast<float>(MY / M);
-                // children: rs-src/nbody.rs:286-301
-                const float cx = __fmul_rn(__fadd_rn(b.x, b.z), 0.5f);
-                const float cy = __fmul_rn(__fadd_rn(b.y, b.w), 0.5f);
-                const int shift = 2 * (kLevels - 1 - level);
-                const int e1 = lower_bound_quadrant(keys, first, first + count, shift, 1u);
-                const int e2 = lower_bound_quadrant(keys, e1, first + count, shift, 2u);
-                const int e3 = lower_bound_quadrant(keys, e2, first + count, shift, 3u);
-                nbounds[c0 + 0] = make_float4(b.x, cy, cx, b.w);   // UL
-                nbounds[c0 + 1] = make_float4(cx, cy, b.z, b.w);   // UR
-                nbounds[c0 + 2] = make_float4(b.x, b.y, cx, cy);   // LL
-                nbounds[c0 + 3] = make_float4(cx, b.y, b.z, cy);   // LR
-                nrange[c0 + 0] = make_int2(first, e1 - first);
-                nrange[c0 + 1] = make_int2(e1, e2 - e1);
-                nrange[c0 + 2] = make_int2(e2, e3 - e2);
-                nrange[c0 + 3] = make_int2(e3, first + count - e3);
-            }
-        }
-        nchild[node] = child;
-        ndata[node] = make_float4(cxm, cym, mass, leaf ? -1.0f : __fsub_rn(b.z, b.x));  // s = x2 - x1 (:341)
-    }
-    // last block to finish publishes the end of the next level
-    __shared__ int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(&st->ticket, 1);
-        is_last = (t == static_cast<int>(gridDim.x) - 1);
-    }
-    __syncthreads();
-    if (is_last && threadIdx.x == 0) {
-        const int nc = min(*reinterpret_cast<volatile int*>(&st->node_count), cap_nodes);
-        st->lvl_begin[level + 2] = nc;
-        st->ticket = 0;
-        __threadfence();
+        (void)cy;
     }
 }
 
@@ -396,12 +458,16 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 }
 
 // ---- traversal, FAST ---------------------------------------------------------------------------------------
+// One warp per 32 Morton-consecutive bodies.  Stack entries are (interior node, mask of lanes that must open
+// it); an opened node's four children (one 64-byte record block) are evaluated inline by the lanes in the
+// mask with the reference's per-body rules (rs-src/nbody.rs:333-377); only children that some lane must open
+// are pushed.  Every body therefore evaluates exactly the reference's interaction list.
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     const float4* __restrict__ ndata, const int* __restrict__ nchild, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
     int i_begin, float theta2, float2* __restrict__ acc, BhStatus* st) {
-    __shared__ unsigned stk[kTravWarps][kStackPerWarp];
+    __shared__ uint2 stk[kTravWarps][kStackPerWarp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * kTravWarps + warp;
     const int li = w * 32 + lane;
@@ -410,46 +476,62 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     const int pos = live ? (mine ? mine[li] : li) : 0;  // position in sorted order
     const float px = sx[pos], py = sy[pos];
     float ax = 0.f, ay = 0.f;
-    int blocked = live ? kNone : -1;
-    unsigned* s = stk[warp];
-    int sp = 1;
-    if (lane == 0) s[0] = 0u;
-    __syncwarp();
+    uint2* s = stk[warp];
+    int sp = 0;
     unsigned long long n_int = 0, n_vis = 0;
-    while (sp > 0) {
-        --sp;
-        const unsigned e = s[sp];
-        __syncwarp();
-        const int node = static_cast<int>(e & 0x3ffffffu), d = static_cast<int>(e >> 26);
-        if (d <= blocked) blocked = kNone;   // the DFS has left the subtree this lane accepted
-        const float4 nd = __ldg(&ndata[node]);
-        const bool active = (blocked == kNone);
+
+    auto interact = [&](const float4& nd, float dx, float dy, float d2) {
+        const float sc = nd.z * rcp_approx(d2 + kEps);
+        ax = fmaf(sc, dx, ax);
+        ay = fmaf(sc, dy, ay);
+        if (COUNT) n_int++;
+    };
+    {   // the root (rs-src/nbody.rs:447 starts compute_force there)
+        const float4 nd = __ldg(&ndata[0]);
         const float dx = nd.x - px, dy = nd.y - py;
         const float d2 = fmaf(dy, dy, dx * dx);
-        if (COUNT) n_vis += active ? 1 : 0;
+        if (COUNT) n_vis += live ? 1 : 0;
         if (nd.w < 0.f) {
-            // leaf (rs-src/nbody.rs:363-374): skip own entry (bitwise position match) and empty nodes
-            if (active && nd.z != 0.f && !(nd.x == px && nd.y == py)) {
-                const float sc = nd.z * rcp_approx(d2 + kEps);
-                ax = fmaf(sc, dx, ax); ay = fmaf(sc, dy, ay);
-                if (COUNT) n_int++;
-            }
+            if (live && nd.z != 0.f && !(nd.x == px && nd.y == py)) interact(nd, dx, dy, d2);
         } else {
-            // interior (:339-361): accept iff s/d < theta  <=>  s^2 < theta^2 d^2
             const bool accept = (nd.w * nd.w) < theta2 * d2;
-            if (active && accept) {
-                const float sc = nd.z * rcp_approx(d2 + kEps);
-                ax = fmaf(sc, dx, ax); ay = fmaf(sc, dy, ay);
-                blocked = d;
-                if (COUNT) n_int++;
-            }
-            if (__any_sync(0xffffffffu, active && !accept)) {
-                const int c = __ldg(&nchild[node]);
-                if (lane < 4) s[sp + 3 - lane] = static_cast<unsigned>(c + lane) | (static_cast<unsigned>(d + 1) << 26);
-                sp += 4;
-                __syncwarp();
+            if (live && accept) interact(nd, dx, dy, d2);
+            const unsigned om = __ballot_sync(0xffffffffu, live && !accept);
+            if (om) {
+                if (lane == 0) s[0] = make_uint2(0u, om);
+                sp = 1;
             }
         }
+        __syncwarp();
+    }
+    while (sp > 0) {
+        --sp;
+        const uint2 e = s[sp];
+        __syncwarp();
+        const bool act = (e.y >> lane) & 1u;
+        const int c = __ldg(&nchild[e.x]);
+        if (COUNT) n_vis += act ? 4 : 0;
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {   // push order 3..0 so that child 0 is opened first (DFS-like order)
+            const float4 nd = __ldg(&ndata[c + k]);
+            if (nd.z == 0.f) continue;   // empty leaf (:367-368), warp-uniform
+            const float dx = nd.x - px, dy = nd.y - py;
+            const float d2 = fmaf(dy, dy, dx * dx);
+            if (nd.w < 0.f) {
+                // leaf (:363-374): skip own entry (bitwise position match)
+                if (act && !(nd.x == px && nd.y == py)) interact(nd, dx, dy, d2);
+            } else {
+                // interior (:339-361): accept iff s/d < theta  <=>  s^2 < theta^2 d^2
+                const bool accept = (nd.w * nd.w) < theta2 * d2;
+                if (act && accept) interact(nd, dx, dy, d2);
+                const unsigned om = __ballot_sync(0xffffffffu, act && !accept);
+                if (om) {
+                    if (lane == 0) s[sp] = make_uint2(static_cast<unsigned>(c + k), om);
+                    sp++;
+                }
+            }
+        }
+        __syncwarp();
     }
     if (live) acc[idx_sorted[pos] - i_begin] = make_float2(ax, ay);
     if (COUNT) {
@@ -539,7 +621,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         auto fr = [](void* p) { if (p) cudaFree(p); };
         fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp);
+        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.cub_tmp);
         const size_t N = static_cast<size_t>(n);
         NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
         NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
@@ -549,10 +631,12 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaMalloc(&w.ndata, sizeof(float4) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nbounds, sizeof(float4) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nchild, sizeof(int) * w.cap_nodes));
-        NB_CUDA(cudaMalloc(&w.nrange, sizeof(int2) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.delta, N)); NB_CUDA(cudaMalloc(&w.dcap, N)); NB_CUDA(cudaMalloc(&w.close, N));
+        NB_CUDA(cudaMalloc(&w.count, N * 4)); NB_CUDA(cudaMalloc(&w.base, N * 4));
         NB_CUDA(cudaMalloc(&w.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
         size_t b1 = 0, b2 = 0, b3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, e.stream);
+        cub::DeviceScan::ExclusiveSum(nullptr, b2, w.count, w.base, n, e.stream);
         cub::DeviceSelect::If(nullptr, b3, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.idx_sorted, 0, n}, e.stream);
         w.cub_bytes = std::max(b1, std::max(b2, b3)) + 256;
         NB_CUDA(cudaMalloc(&w.cub_tmp, w.cub_bytes));
@@ -636,12 +720,13 @@ static void bh_forces(Engine& e, float theta) {
         }
         {
             PhaseScope ps(e, 5);
-            const int grid = e.num_sms * 2;
-            for (int l = 0; l <= kLevels; l++) {
-                bh_build_level_kernel<<<grid, T, 0, s>>>(l, n, w.cap_nodes, w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.ndata,
-                                                        w.nbounds, w.nchild, w.nrange, w.status);
-            }
-            e.ctr.kernel_launches += kLevels + 1;
+            bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, w.delta, w.close);
+            bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
+            size_t tb = w.cub_bytes;
+            cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
+            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.ndata, w.nchild, n, (w.cap_nodes - 4) / 4};
+            bh_emit_kernel<<<G, T, 0, s>>>(ba, w.status);
+            e.ctr.kernel_launches += 3;
         }
         const int* mine = nullptr;
         int n_list = n;
@@ -713,7 +798,7 @@ void bh_shutdown(Engine& e) {
     BhWork& w = work(e);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nrange); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     delete &w;
     e.bh = nullptr;

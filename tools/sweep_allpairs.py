@@ -17,8 +17,8 @@ st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 lib.set_stream(st.cuda_stream)
 lib.set_particles(ic.plummer_2d(n, seed=3))
-for bpt, cps in [(1, 3), (1, 4), (1, 5), (2, 2), (2, 3), (2, 4), (4, 1), (4, 2)]:
-    for waves in (4, 16, 64):
+for bpt, cps in [(1, 3), (1, 4), (1, 5), (2, 2), (2, 3), (2, 4), (4, 2), (4, 3)]:
+    for waves in (16, 64, 128):
         lib.tune(bpt, waves, cps)
         for _ in range(2):
             lib.step_brute_force(0.01)
