@@ -42,6 +42,9 @@ WORKLOADS = {
     "c5": dict(n=1 << 22, kind="bh", theta=0.75, ic="disk", seed=5, desc="4,194,304-body uniform disk, Barnes-Hut theta=0.75"),
 }
 DT = 0.01
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+# `ncu --set full` captures (profiles/r01_ncu_full_*.txt); keyed by (workload, n_gpus)
+TRAFFIC_NCU = {("c3", 1): 28.21e6 + 130.74e6}
 
 
 def make_ic(w):
@@ -177,8 +180,11 @@ def run_reference(args, w):
             o.brute_forces_rows(0, rows)
         el = time.perf_counter() - t0
         value, unit, cores = rows * (n - 1) * args.steps / el, "pair-interactions/s", 1
-        sample = f"per step: forces on {rows} of {n} bodies against all {n}, single thread (the reference's brute force is single-threaded)"
+        sample = f"per step: forces on {rows} of {n} bodies against all {n}, single thread (the reference's brute force is single-threaded, rs-src/nbody.rs:132-144)"
         metric = "pair-interactions/s"
+        t = time.perf_counter(); o.brute_forces_rows(0, min(n, rows * nc // 2), nthreads=nc); dtm = time.perf_counter() - t
+        all_cores = {"value": min(n, rows * nc // 2) * (n - 1) / dtm, "cores": nc,
+                     "note": "NOT the reference: its i loop split over all host threads, for context only"}
     else:
         for _ in range(min(args.warmup, 1)):
             o.step_barnes_hut(w["theta"], DT, nc)
@@ -191,11 +197,13 @@ def run_reference(args, w):
         sample = f"{k} full Barnes-Hut steps, nthreads={nc}"
         metric = "body-steps/s"
         args.steps = k
+        all_cores = None
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {w['desc']}", "dt": DT},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": f"{args.workload}: {w['desc']}", "n_bodies": n, "dt": DT, "ic": w["ic"], "seed": w["seed"]},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                             **({"all_cores_not_in_reference": all_cores} if all_cores else {})},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
@@ -277,6 +285,18 @@ def main():
         step()
         flush.zero_()
     barrier()
+    bh_stats = None
+    if w["kind"] == "bh":
+        # one instrumented step (outside the timed region): interactions and node visits per step
+        lib.bh_count_interactions(True)
+        lib.reset_counters()
+        step()
+        lib.synchronize()
+        c = lib.counters()
+        bh_stats = {"interactions_per_step": c["bh_interactions"], "nodes_visited_per_step": c["bh_nodes_visited"],
+                    "tree_nodes": c["bh_nodes_built"]}
+        lib.bh_count_interactions(False)
+        barrier()
 
     lib.reset_counters()
     lib.phase_timing(True)
@@ -341,7 +361,8 @@ def main():
         per_launch_pairs = (n // world) * (n - 1)
         achieved = per_launch_pairs * FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
         roofline = {"bound": "fp32", "kernel": "allpairs_fast_kernel", "achieved": achieved, "peak": fp32_peak,
-                    "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None,
+                    "traffic": TRAFFIC_NCU.get((args.workload, world)),
                     "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": force_ms, "kernel_share_of_step": force_ms / ms_per_step,
                     "peak_source": f"computed 2*128*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; sm_max_mhz is from it); "
                                    "the kernel is co-limited by the MUFU pipe at 75% of this (DESIGN.md section 4)",
@@ -351,9 +372,23 @@ def main():
         value = n * args.steps / (ms * 1e-3)
         e2e_value = n / e2e_s
         metric, unit = "body-steps/s", "body-steps/s"
-        roofline = {"bound": "hbm", "kernel": "bh_traverse", "achieved": None, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
-                    "frac": None, "traffic": None}
-        extra = {"bh_steps_per_s": args.steps / (ms * 1e-3)}
+        trav_ms = phases["force"]
+        vis, inter = bh_stats["nodes_visited_per_step"], bh_stats["interactions_per_step"]
+        if world > 1:
+            t2 = torch.tensor([vis, inter], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t2)
+            vis, inter = int(t2[0].item()), int(t2[1].item())
+        # traversal moves 32 B per visited node + 48 B per body (algorithmic); per rank launch
+        alg_bytes = (32 * vis + 48 * n) / world
+        achieved = alg_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else None
+        hbm = pk.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "hbm", "kernel": "bh_traverse_fast_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                    "frac": achieved / hbm if achieved else None, "traffic": None, "kernel_ms": trav_ms,
+                    "kernel_share_of_step": trav_ms / ms_per_step,
+                    "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in pk else "fallback 6.65 TB/s") +
+                                   "; node records are L1/L2-served (ncu: DRAM <1%), the walk is issue-bound -- a low HBM fraction is expected (DESIGN.md 4.3)"}
+        extra = {"bh_steps_per_s": args.steps / (ms * 1e-3), "bh_interactions_per_s": inter * args.steps / (ms * 1e-3),
+                 "bh": bh_stats}
 
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

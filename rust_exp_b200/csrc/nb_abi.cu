@@ -177,6 +177,7 @@ int32_t nbx_synchronize(void) {
         set_error("cudaStreamSynchronize: %s", cudaGetErrorString(err));
         return -1;
     }
+    bh_poll(e);
     return 0;
 }
 
@@ -200,10 +201,12 @@ int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_p
 
 void nbx_get_counters(nbx_counters* out) {
     NB_LOCK();
+    if (engine().inited) bh_poll(engine());
     *out = engine().ctr;
 }
 void nbx_reset_counters(void) {
     NB_LOCK();
+    if (engine().inited) bh_poll(engine());
     engine().ctr = nbx_counters{};
 }
 int32_t nbx_bh_count_interactions(int32_t enable) {

@@ -77,6 +77,8 @@ struct BhWork {
     float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
     int cap_acc = 0;
     bool warned = false;
+    bool status_pending = false;
+    cudaEvent_t status_ev = nullptr;
 };
 
 static BhWork& work(Engine& e) {
@@ -615,6 +617,8 @@ struct InRange {
 };
 using Iota = thrust::counting_iterator<int>;
 
+static void check_status(Engine& e, struct BhWork& w, bool sync_now);
+
 // ---- host orchestration ----------------------------------------------------------------------------------------
 static void ensure_work(Engine& e, BhWork& w, int n) {
     if (n > w.cap_n) {
@@ -649,6 +653,7 @@ static void ensure_status(BhWork& w) {
         NB_CUDA(cudaMalloc(&w.status, sizeof(BhStatus)));
         NB_CUDA(cudaMallocHost(&w.status_host, sizeof(BhStatus)));
         memset(w.status_host, 0, sizeof(BhStatus));
+        NB_CUDA(cudaEventCreateWithFlags(&w.status_ev, cudaEventDisableTiming));
     }
 }
 
@@ -666,6 +671,7 @@ static GlobalPos global_positions(Engine& e) {
 static void bh_forces(Engine& e, float theta) {
     BhWork& w = work(e);
     ensure_status(w);
+    check_status(e, w, false);   // previous step's status (its copy has long finished by now)
     const int n = e.n;
     ensure_work(e, w, n);
     const int nl = local_count(e), ib = local_begin(e);
@@ -750,11 +756,17 @@ static void bh_forces(Engine& e, float theta) {
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
+    NB_CUDA(cudaEventRecord(w.status_ev, s));
+    w.status_pending = true;
 }
 
-static void check_status(Engine& e, BhWork& w) {
-    // deferred: looks at the status of the step that has just been enqueued (one stream sync per BH step)
-    NB_CUDA(cudaStreamSynchronize(e.stream));
+// Deferred: the status block of a step is copied to pinned memory behind the step and looked at when the
+// NEXT Barnes-Hut call (or any synchronising call) arrives, so stepping never stalls the host on the GPU.
+static void check_status(Engine& e, BhWork& w, bool sync_now) {
+    if (!w.status_pending) return;
+    if (sync_now) NB_CUDA(cudaEventSynchronize(w.status_ev));
+    else if (cudaEventQuery(w.status_ev) != cudaSuccess) { (void)cudaGetLastError(); NB_CUDA(cudaEventSynchronize(w.status_ev)); }
+    w.status_pending = false;
     const BhStatus& h = *w.status_host;
     if (h.depth_error) fatal("Node::insert() - recursion depth > 50 (the reference panics here, rs-src/nbody.rs:230-232)", __FILE__, __LINE__);
     if (h.overflow && !w.warned) {
@@ -764,6 +776,9 @@ static void check_status(Engine& e, BhWork& w) {
     e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
     e.ctr.bh_interactions += h.interactions;
     e.ctr.bh_nodes_visited += h.visited;
+}
+void bh_poll(Engine& e) {
+    if (e.bh) check_status(e, work(e), true);
 }
 
 void bh_step(Engine& e, float theta, float dt) {
@@ -779,7 +794,6 @@ void bh_step(Engine& e, float theta, float dt) {
     dist_signal_step_done(e);
     e.ctr.steps++;
     if (e.phase_timing) e.ev_slot++;
-    check_status(e, w);
 }
 
 void bh_accelerations(Engine& e, float theta, float2* out) {
@@ -790,7 +804,7 @@ void bh_accelerations(Engine& e, float theta, float2* out) {
     else launch_accel_from_partial(e, w.acc, 1, out);
     e.step_count++;
     dist_signal_step_done(e);
-    check_status(e, w);
+    check_status(e, w, true);
 }
 
 void bh_shutdown(Engine& e) {
@@ -800,6 +814,7 @@ void bh_shutdown(Engine& e) {
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
     fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
+    if (w.status_ev) cudaEventDestroy(w.status_ev);
     delete &w;
     e.bh = nullptr;
 }

@@ -198,6 +198,7 @@ int dist_nccl_init(Engine& e, const void* id128);
 void bh_step(Engine& e, float theta, float dt);
 void bh_accelerations(Engine& e, float theta, float2* out);
 void bh_shutdown(Engine& e);
+void bh_poll(Engine& e);   // fold the last Barnes-Hut step's status/counters in (synchronises)
 
 // nb_draw.cu
 void draw_to_host(Engine& e, int w, int h, uint32_t* fb);
