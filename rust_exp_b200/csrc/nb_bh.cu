@@ -50,7 +50,7 @@ struct BhStatus {
     int lvl_begin[kLevels + 3];
     int aabb_enc[4];          // ordered-int encodings of x1,y1 (min) and x2,y2 (max)
     int n_mine;
-    int pad;
+    int n_interior;
     unsigned long long interactions;
     unsigned long long visited;
 };
@@ -71,7 +71,7 @@ struct BhWork {
     int* nchild = nullptr;     // first of 4 children, -1 for a leaf
     signed char *delta = nullptr, *dcap = nullptr;
     unsigned char* close = nullptr;
-    int *count = nullptr, *base = nullptr;
+    int *count = nullptr, *base = nullptr, *owner = nullptr;
     BhStatus* status = nullptr;
     BhStatus* status_host = nullptr;
     float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
@@ -298,17 +298,19 @@ __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int le
     return a.base[first] + (level - dl - 1);
 }
 
-__global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
+// owner[id] = first body of interior node id (one thread per body; bodies start 0.76 nodes on average)
+__global__ void bh_owner_kernel(const BuildArgs a, int* __restrict__ owner, BhStatus* st) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
-    const size_t stride = static_cast<size_t>(a.n) + 1;
-    const float rx1 = ord2f(st->aabb_enc[0]), ry1 = ord2f(st->aabb_enc[1]);
-    const float rx2 = ord2f(st->aabb_enc[2]), ry2 = ord2f(st->aabb_enc[3]);
     const int dhi = a.dcap[i];
     const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
+    const int b = a.base[i];
+    for (int k = 0; k < dhi - dlo && b + k < a.cap_interior; k++) owner[b + k] = i;
     if (i == 0) {
-        st->node_count = 1 + 4 * min(a.base[a.n - 1], a.cap_interior);   // count[n-1] == 0
-        if (a.base[a.n - 1] > a.cap_interior) st->overflow = 1;
+        const int total = a.base[a.n - 1];   // count[n-1] == 0
+        st->node_count = 1 + 4 * min(total, a.cap_interior);
+        st->n_interior = min(total, a.cap_interior);
+        if (total > a.cap_interior) st->overflow = 1;
         if (dhi < 0) {
             // no interior node at all: the root is a leaf (one body, or everything merges)
             float cx = 0.f, cy = 0.f, mm = 0.f;
@@ -317,10 +319,19 @@ __global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
             a.nchild[0] = -1;
         }
     }
-    const unsigned long long key = a.keys[i];
-    for (int l = dlo + 1; l <= dhi; l++) {
-        const int id = a.base[i] + (l - dlo - 1);
-        if (id >= a.cap_interior) break;
+}
+
+// one thread per interior node
+__global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner, const BhStatus* st) {
+    const int T = st->n_interior;
+    const size_t stride = static_cast<size_t>(a.n) + 1;
+    const float rx1 = ord2f(st->aabb_enc[0]), ry1 = ord2f(st->aabb_enc[1]);
+    const float rx2 = ord2f(st->aabb_enc[2]), ry2 = ord2f(st->aabb_enc[3]);
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < T; id += gridDim.x * blockDim.x) {
+        const int i = owner[id];
+        const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
+        const int l = dlo + 1 + (id - a.base[i]);
+        const unsigned long long key = a.keys[i];
         // cell bounds at level l: replay the key bits through rs-src/nbody.rs:286-301
         float x1 = rx1, y1 = ry1, x2 = rx2, y2 = ry2;
         for (int t = 0; t < l; t++) {
@@ -330,13 +341,15 @@ __global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
             if (q & 2u) y2 = cy; else y1 = cy;      // LL/LR: lower half
         }
         const int shift = 2 * (kLevels - 1 - l);
-        // end of this cell's range: first body whose level-l prefix differs
+        // end of this cell's range: first body whose level-l prefix differs (galloping, then bisection)
         int end;
         if (l == 0) {
             end = a.n;
         } else {
             const unsigned long long pre = key >> (shift + 2);
-            int lo = i + 1, hi = a.n;
+            int lo = i + 1, step = 2;
+            int hi = min(a.n, lo + step);
+            while (hi < a.n && (a.keys[hi - 1] >> (shift + 2)) == pre) { lo = hi; step <<= 1; hi = min(a.n, lo + step); }
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if ((a.keys[mid] >> (shift + 2)) == pre) lo = mid + 1; else hi = mid;
@@ -347,7 +360,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
         const int e2 = lower_bound_quadrant(a.keys, e1, end, shift, 2u);
         const int e3 = lower_bound_quadrant(a.keys, e2, end, shift, 3u);
         const int f[5] = {i, e1, e2, e3, end};
-        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f), cy = __fmul_rn(__fadd_rn(y1, y2), 0.5f);
+        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f);
         const int blk = 4 + 4 * id;
         if (l == 0) {   // the root's own record
             const double M = a.p3[a.n] - a.p3[0];
@@ -356,13 +369,15 @@ __global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
                                      static_cast<float>(M), __fsub_rn(x2, x1));
             a.nchild[0] = blk;
         }
+        float4 rec[4];
+        int4 ch = make_int4(-1, -1, -1, -1);
+        int* chp = &ch.x;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const int first = f[q], cnt = f[q + 1] - f[q];
-            float4 rec = make_float4(0.f, 0.f, 0.f, -1.0f);
-            int child = -1;
+            rec[q] = make_float4(0.f, 0.f, 0.f, -1.0f);
             if (cnt == 1) {
-                rec = make_float4(a.sx[first], a.sy[first], a.sm[first], -1.0f);   // exact copy (:305-311)
+                rec[q] = make_float4(a.sx[first], a.sy[first], a.sm[first], -1.0f);   // exact copy (:305-311)
             } else if (cnt >= 2) {
                 int cid = -1;
                 if (static_cast<int>(a.dcap[first]) >= l + 1) {
@@ -375,18 +390,18 @@ __global__ void bh_emit_kernel(const BuildArgs a, BhStatus* st) {
                     const double MY = a.p3[2 * stride + first + cnt] - a.p3[2 * stride + first];
                     // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
-                    rec = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
-                    child = 4 + 4 * cid;
+                    rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
+                    chp[q] = 4 + 4 * cid;
                 } else {
                     float bx = 0.f, by = 0.f, bm = 0.f;
                     for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
-                    rec = make_float4(bx, by, bm, -1.0f);
+                    rec[q] = make_float4(bx, by, bm, -1.0f);
                 }
             }
-            a.ndata[blk + q] = rec;
-            a.nchild[blk + q] = child;
         }
-        (void)cy;
+#pragma unroll
+        for (int q = 0; q < 4; q++) a.ndata[blk + q] = rec[q];
+        *reinterpret_cast<int4*>(a.nchild + blk) = ch;
     }
 }
 
@@ -625,7 +640,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         auto fr = [](void* p) { if (p) cudaFree(p); };
         fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.cub_tmp);
+        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp);
         const size_t N = static_cast<size_t>(n);
         NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
         NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
@@ -637,6 +652,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaMalloc(&w.nchild, sizeof(int) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.delta, N)); NB_CUDA(cudaMalloc(&w.dcap, N)); NB_CUDA(cudaMalloc(&w.close, N));
         NB_CUDA(cudaMalloc(&w.count, N * 4)); NB_CUDA(cudaMalloc(&w.base, N * 4));
+        NB_CUDA(cudaMalloc(&w.owner, sizeof(int) * (w.cap_nodes / 4)));
         NB_CUDA(cudaMalloc(&w.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
         size_t b1 = 0, b2 = 0, b3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, e.stream);
@@ -731,8 +747,9 @@ static void bh_forces(Engine& e, float theta) {
             size_t tb = w.cub_bytes;
             cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
             BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.ndata, w.nchild, n, (w.cap_nodes - 4) / 4};
-            bh_emit_kernel<<<G, T, 0, s>>>(ba, w.status);
-            e.ctr.kernel_launches += 3;
+            bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
+            bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
+            e.ctr.kernel_launches += 4;
         }
         const int* mine = nullptr;
         int n_list = n;
@@ -812,7 +829,7 @@ void bh_shutdown(Engine& e) {
     BhWork& w = work(e);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
     delete &w;
