@@ -68,7 +68,9 @@ struct BhWork {
     int cap_nodes = 0;
     float4* ndata = nullptr;   // com.x, com.y, mass, width (s = x2-x1; < 0 marks a leaf)
     float4* nbounds = nullptr; // x1,y1,x2,y2
-    int* nchild = nullptr;     // first of 4 children, -1 for a leaf
+    int* nchild = nullptr;     // first of 4 children, -1 for a leaf   (ndata/nbounds/nchild: EXACT mode, AoS)
+    float4* nblk = nullptr;    // FAST mode: block-SoA records
+    int4* ncblk = nullptr;
     signed char *delta = nullptr, *dcap = nullptr;
     unsigned char* close = nullptr;
     int *count = nullptr, *base = nullptr, *owner = nullptr;
@@ -120,7 +122,16 @@ __global__ void bh_aabb_kernel(const float* __restrict__ x, const float* __restr
         mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
         mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
     }
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ int red[4][8];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][wid] = mnx; red[1][wid] = mny; red[2][wid] = mxx; red[3][wid] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; k++) {
+            mnx = min(mnx, red[0][k]); mny = min(mny, red[1][k]);
+            mxx = max(mxx, red[2][k]); mxy = max(mxy, red[3][k]);
+        }
         atomicMin(&st->aabb_enc[0], mnx);
         atomicMin(&st->aabb_enc[1], mny);
         atomicMax(&st->aabb_enc[2], mxx);
@@ -188,12 +199,24 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const doub
     const double t = BR(tmp).Sum(v);
     if (threadIdx.x == 0) tile_sums[blockIdx.y * ntiles + blockIdx.x] = t;
 }
-__global__ void scan_tile_offsets_kernel(double* tile_sums, int ntiles) {
-    // one thread per array: sequential, fixed order (ntiles <= a few thousand)
-    if (threadIdx.x == 0) {
-        double* t = tile_sums + blockIdx.x * ntiles;
-        double run = 0.0;
-        for (int i = 0; i < ntiles; i++) { const double v = t[i]; t[i] = run; run += v; }
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(double* tile_sums, int ntiles) {
+    // one block per array: chunks of kScanThreads tiles, fixed block-scan tree + a sequential carry
+    using BS = cub::BlockScan<double, kScanThreads>;
+    __shared__ typename BS::TempStorage tmp;
+    __shared__ double carry;
+    double* t = tile_sums + blockIdx.x * ntiles;
+    if (threadIdx.x == 0) carry = 0.0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += kScanThreads) {
+        const int i = base + threadIdx.x;
+        const double v = i < ntiles ? t[i] : 0.0;
+        double ex, total;
+        BS(tmp).ExclusiveSum(v, ex, total);
+        const double c = carry;
+        if (i < ntiles) t[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
     }
 }
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const double* __restrict__ in, double* __restrict__ out, int len,
@@ -287,8 +310,8 @@ struct BuildArgs {
     const double* p3;
     const signed char* dcap;
     const int* base;      // exclusive prefix of count[]
-    float4* ndata;
-    int* nchild;
+    float4* nblk;     // block-SoA node records: block b = {x[4], y[4], m[4], s[4]} at nblk[4b .. 4b+3]
+    int4* ncblk;      // child block index of each of the 4 nodes of block b (-1 = leaf)
     int n, cap_interior;
 };
 
@@ -315,8 +338,11 @@ __global__ void bh_owner_kernel(const BuildArgs a, int* __restrict__ owner, BhSt
             // no interior node at all: the root is a leaf (one body, or everything merges)
             float cx = 0.f, cy = 0.f, mm = 0.f;
             for (int k = 0; k < a.n; k++) add_mass_ref(cx, cy, mm, a.sx[k], a.sy[k], a.sm[k]);
-            a.ndata[0] = make_float4(cx, cy, mm, -1.0f);
-            a.nchild[0] = -1;
+            a.nblk[0] = make_float4(cx, 0.f, 0.f, 0.f);
+            a.nblk[1] = make_float4(cy, 0.f, 0.f, 0.f);
+            a.nblk[2] = make_float4(mm, 0.f, 0.f, 0.f);
+            a.nblk[3] = make_float4(-1.f, -1.f, -1.f, -1.f);
+            a.ncblk[0] = make_int4(-1, -1, -1, -1);
         }
     }
 }
@@ -361,13 +387,14 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
         const int e3 = lower_bound_quadrant(a.keys, e2, end, shift, 3u);
         const int f[5] = {i, e1, e2, e3, end};
         const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f);
-        const int blk = 4 + 4 * id;
+        const int blk = 1 + id;   // block 0 holds the root (slot 0; slots 1..3 are empty leaves)
         if (l == 0) {   // the root's own record
             const double M = a.p3[a.n] - a.p3[0];
-            a.ndata[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M),
-                                     static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M),
-                                     static_cast<float>(M), __fsub_rn(x2, x1));
-            a.nchild[0] = blk;
+            a.nblk[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M), 0.f, 0.f, 0.f);
+            a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
+            a.nblk[2] = make_float4(static_cast<float>(M), 0.f, 0.f, 0.f);
+            a.nblk[3] = make_float4(__fsub_rn(x2, x1), -1.f, -1.f, -1.f);
+            a.ncblk[0] = make_int4(blk, -1, -1, -1);
         }
         float4 rec[4];
         int4 ch = make_int4(-1, -1, -1, -1);
@@ -391,7 +418,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                     // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
                     rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
-                    chp[q] = 4 + 4 * cid;
+                    chp[q] = 1 + cid;
                 } else {
                     float bx = 0.f, by = 0.f, bm = 0.f;
                     for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
@@ -399,9 +426,11 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                 }
             }
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++) a.ndata[blk + q] = rec[q];
-        *reinterpret_cast<int4*>(a.nchild + blk) = ch;
+        a.nblk[4 * blk + 0] = make_float4(rec[0].x, rec[1].x, rec[2].x, rec[3].x);
+        a.nblk[4 * blk + 1] = make_float4(rec[0].y, rec[1].y, rec[2].y, rec[3].y);
+        a.nblk[4 * blk + 2] = make_float4(rec[0].z, rec[1].z, rec[2].z, rec[3].z);
+        a.nblk[4 * blk + 3] = make_float4(rec[0].w, rec[1].w, rec[2].w, rec[3].w);
+        a.ncblk[blk] = ch;
     }
 }
 
@@ -475,13 +504,16 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 }
 
 // ---- traversal, FAST ---------------------------------------------------------------------------------------
-// One warp per 32 Morton-consecutive bodies.  Stack entries are (interior node, mask of lanes that must open
-// it); an opened node's four children (one 64-byte record block) are evaluated inline by the lanes in the
-// mask with the reference's per-body rules (rs-src/nbody.rs:333-377); only children that some lane must open
-// are pushed.  Every body therefore evaluates exactly the reference's interaction list.
+// One warp per 32 Morton-consecutive bodies.  Stack entries are (node block, mask of lanes that must look at
+// it).  A block is the four children of an opened node in SoA form (x[4] y[4] m[4] s[4], 64 bytes): the warp
+// evaluates all four branch-free with packed FP32 -- a lane in the mask interacts with a child if it is a
+// leaf or passes the reference's per-body opening test (rs-src/nbody.rs:345), otherwise it asks for the
+// child to be opened; only children that some lane must open are pushed, with that lane mask.  Every body
+// therefore evaluates exactly the reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and
+// the body's own leaf (d = 0, :365) need no test: their contribution is an exact zero because EPS > 0.
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
-    const float4* __restrict__ ndata, const int* __restrict__ nchild, const float* __restrict__ sx,
+    const float4* __restrict__ nblk, const int4* __restrict__ ncblk, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
     int i_begin, float theta2, float2* __restrict__ acc, BhStatus* st) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
@@ -492,65 +524,63 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     const bool live = li < n_list;
     const int pos = live ? (mine ? mine[li] : li) : 0;  // position in sorted order
     const float px = sx[pos], py = sy[pos];
-    float ax = 0.f, ay = 0.f;
+    const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
+    const float2 eps2 = make_float2(kEps, kEps), th2 = make_float2(theta2, theta2);
+    float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
     uint2* s = stk[warp];
     int sp = 0;
     unsigned long long n_int = 0, n_vis = 0;
-
-    auto interact = [&](const float4& nd, float dx, float dy, float d2) {
-        const float sc = nd.z * rcp_approx(d2 + kEps);
-        ax = fmaf(sc, dx, ax);
-        ay = fmaf(sc, dy, ay);
-        if (COUNT) n_int++;
-    };
-    {   // the root (rs-src/nbody.rs:447 starts compute_force there)
-        const float4 nd = __ldg(&ndata[0]);
-        const float dx = nd.x - px, dy = nd.y - py;
-        const float d2 = fmaf(dy, dy, dx * dx);
-        if (COUNT) n_vis += live ? 1 : 0;
-        if (nd.w < 0.f) {
-            if (live && nd.z != 0.f && !(nd.x == px && nd.y == py)) interact(nd, dx, dy, d2);
-        } else {
-            const bool accept = (nd.w * nd.w) < theta2 * d2;
-            if (live && accept) interact(nd, dx, dy, d2);
-            const unsigned om = __ballot_sync(0xffffffffu, live && !accept);
-            if (om) {
-                if (lane == 0) s[0] = make_uint2(0u, om);
-                sp = 1;
-            }
-        }
+    {
+        const unsigned m0 = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s[0] = make_uint2(0u, m0);   // block 0 = {root, empty, empty, empty}
+        sp = 1;
         __syncwarp();
+        if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
     }
     while (sp > 0) {
         --sp;
         const uint2 e = s[sp];
         __syncwarp();
         const bool act = (e.y >> lane) & 1u;
-        const int c = __ldg(&nchild[e.x]);
-        if (COUNT) n_vis += act ? 4 : 0;
-#pragma unroll
-        for (int k = 3; k >= 0; k--) {   // push order 3..0 so that child 0 is opened first (DFS-like order)
-            const float4 nd = __ldg(&ndata[c + k]);
-            if (nd.z == 0.f) continue;   // empty leaf (:367-368), warp-uniform
-            const float dx = nd.x - px, dy = nd.y - py;
-            const float d2 = fmaf(dy, dy, dx * dx);
-            if (nd.w < 0.f) {
-                // leaf (:363-374): skip own entry (bitwise position match)
-                if (act && !(nd.x == px && nd.y == py)) interact(nd, dx, dy, d2);
-            } else {
-                // interior (:339-361): accept iff s/d < theta  <=>  s^2 < theta^2 d^2
-                const bool accept = (nd.w * nd.w) < theta2 * d2;
-                if (act && accept) interact(nd, dx, dy, d2);
-                const unsigned om = __ballot_sync(0xffffffffu, act && !accept);
-                if (om) {
-                    if (lane == 0) s[sp] = make_uint2(static_cast<unsigned>(c + k), om);
-                    sp++;
-                }
-            }
+        const float4 X = __ldg(&nblk[4 * e.x + 0]), Y = __ldg(&nblk[4 * e.x + 1]);
+        const float4 M = __ldg(&nblk[4 * e.x + 2]), S = __ldg(&nblk[4 * e.x + 3]);
+        const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
+        const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+        const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
+        const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
+        const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
+        // opening test s/d < theta  <=>  s^2 < theta^2 d^2   (s < 0 marks a leaf)
+        const float2 t01 = __fmul2_rn(th2, d01), t23 = __fmul2_rn(th2, d23);
+        const float2 q01 = __fmul2_rn(make_float2(S.x, S.y), make_float2(S.x, S.y));
+        const float2 q23 = __fmul2_rn(make_float2(S.z, S.w), make_float2(S.z, S.w));
+        const bool l0 = S.x < 0.f, l1 = S.y < 0.f, l2 = S.z < 0.f, l3 = S.w < 0.f;
+        const bool a0 = q01.x < t01.x, a1 = q01.y < t01.y, a2 = q23.x < t23.x, a3 = q23.y < t23.y;
+        const bool u0 = act && (l0 || a0), u1 = act && (l1 || a1), u2 = act && (l2 || a2), u3 = act && (l3 || a3);
+        float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
+        float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
+        c01.x = u0 ? c01.x : 0.f; c01.y = u1 ? c01.y : 0.f;
+        c23.x = u2 ? c23.x : 0.f; c23.y = u3 ? c23.y : 0.f;
+        ax = __ffma2_rn(c01, dx01, ax); ay = __ffma2_rn(c01, dy01, ay);
+        ax = __ffma2_rn(c23, dx23, ax); ay = __ffma2_rn(c23, dy23, ay);
+        const unsigned ob = (act && !l0 && !a0 ? 1u : 0u) | (act && !l1 && !a1 ? 2u : 0u) |
+                            (act && !l2 && !a2 ? 4u : 0u) | (act && !l3 && !a3 ? 8u : 0u);
+        if (COUNT) {
+            n_vis += act ? 4 : 0;
+            n_int += (u0 && M.x != 0.f && !(X.x == px && Y.x == py)) + (u1 && M.y != 0.f && !(X.y == px && Y.y == py)) +
+                     (u2 && M.z != 0.f && !(X.z == px && Y.z == py)) + (u3 && M.w != 0.f && !(X.w == px && Y.w == py));
+        }
+        const unsigned any = __reduce_or_sync(0xffffffffu, ob);
+        if (any) {
+            const int4 C = __ldg(&ncblk[e.x]);
+            // push order 3..0 so that child 0 is opened first (DFS-like order)
+            if (any & 8u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 8u); if (lane == 0) s[sp] = make_uint2(C.w, om); sp++; }
+            if (any & 4u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 4u); if (lane == 0) s[sp] = make_uint2(C.z, om); sp++; }
+            if (any & 2u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 2u); if (lane == 0) s[sp] = make_uint2(C.y, om); sp++; }
+            if (any & 1u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 1u); if (lane == 0) s[sp] = make_uint2(C.x, om); sp++; }
         }
         __syncwarp();
     }
-    if (live) acc[idx_sorted[pos] - i_begin] = make_float2(ax, ay);
+    if (live) acc[idx_sorted[pos] - i_begin] = make_float2(ax.x + ax.y, ay.x + ay.y);
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
             n_int += __shfl_xor_sync(0xffffffffu, n_int, o);
@@ -640,7 +670,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         auto fr = [](void* p) { if (p) cudaFree(p); };
         fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp);
+        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp);
         const size_t N = static_cast<size_t>(n);
         NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
         NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
@@ -650,6 +680,8 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaMalloc(&w.ndata, sizeof(float4) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nbounds, sizeof(float4) * w.cap_nodes));
         NB_CUDA(cudaMalloc(&w.nchild, sizeof(int) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.nblk, sizeof(float4) * w.cap_nodes));
+        NB_CUDA(cudaMalloc(&w.ncblk, sizeof(int4) * (w.cap_nodes / 4)));
         NB_CUDA(cudaMalloc(&w.delta, N)); NB_CUDA(cudaMalloc(&w.dcap, N)); NB_CUDA(cudaMalloc(&w.close, N));
         NB_CUDA(cudaMalloc(&w.count, N * 4)); NB_CUDA(cudaMalloc(&w.base, N * 4));
         NB_CUDA(cudaMalloc(&w.owner, sizeof(int) * (w.cap_nodes / 4)));
@@ -736,7 +768,7 @@ static void bh_forces(Engine& e, float theta) {
             const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
             const size_t stride = static_cast<size_t>(n) + 1;
             scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, len, stride, w.tile_sums, ntiles);
-            scan_tile_offsets_kernel<<<3, 32, 0, s>>>(w.tile_sums, ntiles);
+            scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(w.tile_sums, ntiles);
             scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, w.p3, len, stride, w.tile_sums, ntiles);
             e.ctr.kernel_launches += 3;
         }
@@ -746,7 +778,7 @@ static void bh_forces(Engine& e, float theta) {
             bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
             size_t tb = w.cub_bytes;
             cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
-            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.ndata, w.nchild, n, (w.cap_nodes - 4) / 4};
+            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4};
             bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
             bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
             e.ctr.kernel_launches += 4;
@@ -763,10 +795,10 @@ static void bh_forces(Engine& e, float theta) {
         if (n_list > 0) {
             const int blocks = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
             if (e.bh_count)
-                bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, s>>>(w.ndata, w.nchild, w.sx, w.sy, w.idx_sorted, mine,
+                bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, s>>>(w.nblk, w.ncblk, w.sx, w.sy, w.idx_sorted, mine,
                                                                                 n_list, ib, theta * theta, w.acc, w.status);
             else
-                bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, s>>>(w.ndata, w.nchild, w.sx, w.sy, w.idx_sorted, mine,
+                bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, s>>>(w.nblk, w.ncblk, w.sx, w.sy, w.idx_sorted, mine,
                                                                                  n_list, ib, theta * theta, w.acc, w.status);
             e.ctr.kernel_launches++;
         }
@@ -829,7 +861,7 @@ void bh_shutdown(Engine& e) {
     BhWork& w = work(e);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
     delete &w;
