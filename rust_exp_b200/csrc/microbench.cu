@@ -15,21 +15,23 @@ constexpr int kUnroll = 8;
 
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-enum Test { T_FFMA = 0, T_FFMA2, T_FADD, T_FADD2, T_FMUL2, T_MUFU, T_PAIR_SCALAR, T_PAIR_X2, T_MUFU_FFMA2_MIX, T_COUNT };
-static const char* kNames[T_COUNT] = {"ffma", "ffma2", "fadd", "fadd2", "fmul2", "mufu_rcp", "pair_scalar", "pair_x2", "mufu+3.5ffma2"};
+enum Test { T_FFMA = 0, T_FFMA2, T_FADD, T_FADD2, T_FMUL2, T_MUFU, T_PAIR_SCALAR, T_PAIR_X2, T_MUFU_FFMA2_MIX, T_FFMA2_PLUS_FFMA, T_FFMA2_PLUS_FADD, T_FFMA2_PLUS_IMAD, T_COUNT };
+static const char* kNames[T_COUNT] = {"ffma", "ffma2", "fadd", "fadd2", "fmul2", "mufu_rcp", "pair_scalar", "pair_x2", "mufu+3.5ffma2", "ffma2+ffma(1:1)", "ffma2+fadd(1:1)", "ffma2+imad(1:1)"};
 // lane-ops (per thread per inner iteration) and flop per lane-op for reporting
-static const double kOpsPerIter[T_COUNT] = {kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll};
+static const double kOpsPerIter[T_COUNT] = {kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll, kUnroll};
 
 template <int T>
 __global__ void __launch_bounds__(256) bench_kernel(float* out, long long* cycles, float seed) {
     float a[kUnroll], b[kUnroll];
     float2 a2[kUnroll], b2[kUnroll];
+    int ia[kUnroll];
 #pragma unroll
     for (int k = 0; k < kUnroll; k++) {
         a[k] = seed + k + threadIdx.x * 1e-3f;
         b[k] = seed * 0.5f + k;
         a2[k] = make_float2(a[k], a[k] + 1.f);
         b2[k] = make_float2(b[k], b[k] + 1.f);
+        ia[k] = threadIdx.x + k;
     }
     const float c = seed * 1.0001f, d = seed * 0.999f;
     const float2 c2 = make_float2(c, d), d2 = make_float2(d, c);
@@ -62,6 +64,9 @@ __global__ void __launch_bounds__(256) bench_kernel(float* out, long long* cycle
                 a2[k] = __ffma2_rn(s, dx, a2[k]);
                 b2[k] = __ffma2_rn(s, dy, b2[k]);
             }
+            if (T == T_FFMA2_PLUS_FFMA) { a2[k] = __ffma2_rn(a2[k], c2, d2); a[k] = fmaf(a[k], c, d); }
+            if (T == T_FFMA2_PLUS_FADD) { a2[k] = __ffma2_rn(a2[k], c2, d2); a[k] = a[k] + c; }
+            if (T == T_FFMA2_PLUS_IMAD) { a2[k] = __ffma2_rn(a2[k], c2, d2); ia[k] = ia[k] * 3 + it; }
             if (T == T_MUFU_FFMA2_MIX) {
                 a[k] = rcp_approx(a[k]);
                 a2[k] = __ffma2_rn(a2[k], c2, d2);
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(256) bench_kernel(float* out, long long* cycle
     const long long t1 = clock64();
     float acc = 0.f;
 #pragma unroll
-    for (int k = 0; k < kUnroll; k++) acc += a[k] + b[k] + a2[k].x + a2[k].y + b2[k].x + b2[k].y;
+    for (int k = 0; k < kUnroll; k++) acc += a[k] + b[k] + a2[k].x + a2[k].y + b2[k].x + b2[k].y + (float)ia[k];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
 }
@@ -119,7 +124,7 @@ int main() {
     CK(cudaMalloc(&cyc, sizeof(long long) * sms * 8));
     // "units": ffma/fadd = lane-instructions (x2 forms = one unit per packed instruction, i.e. 2 lane-results);
     // mufu = lane-results; pair_scalar = pairs; pair_x2 = 2 pairs per unit.
-    for (int bps : {4, 8}) {
+    for (int bps : {4}) {
         run<T_FFMA>(sms, bps, out, cyc);
         run<T_FFMA2>(sms, bps, out, cyc);
         run<T_FADD>(sms, bps, out, cyc);
@@ -129,6 +134,9 @@ int main() {
         run<T_PAIR_SCALAR>(sms, bps, out, cyc);
         run<T_PAIR_X2>(sms, bps, out, cyc);
         run<T_MUFU_FFMA2_MIX>(sms, bps, out, cyc);
+        run<T_FFMA2_PLUS_FFMA>(sms, bps, out, cyc);
+        run<T_FFMA2_PLUS_FADD>(sms, bps, out, cyc);
+        run<T_FFMA2_PLUS_IMAD>(sms, bps, out, cyc);
     }
     return 0;
 }

@@ -196,6 +196,7 @@ int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_p
     e.tune.bodies_per_thread = bodies_per_thread;
     e.tune.target_waves = target_waves;
     e.tune.ctas_per_sm = ctas_per_sm;
+    if (const char* sh = getenv("NB_SHARE_RCP")) e.tune.share_rcp = atoi(sh);   // experiment knob
     return 0;
 }
 

@@ -24,6 +24,7 @@ namespace nb {
 
 constexpr int kTJ = 512;             // j bodies per shared-memory tile
 constexpr int kStages = 3;           // TMA ring depth
+constexpr int kDefaultShare = 0;     // reciprocal sharing (see pair4_shared_rcp); measured choice
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
 constexpr int kThreads = kComputeThreads + 32;  // + 1 producer warp
@@ -53,6 +54,24 @@ __device__ __forceinline__ void pair2(float xa, float xb, float ya, float yb, fl
     ay = __ffma2_rn(s, dy, ay);
 }
 
+// Four pairs (one i body against j bodies a,b,c,d) sharing TWO reciprocals: with A = (d2a,d2b), B = (d2c,d2d),
+// R = rcp(A*B) gives 1/A = R*B and 1/B = R*A -- 3 extra FMUL2 (6 FMA-pipe cycles) buy back 2 MUFU.RCP
+// (16 MUFU-pipe cycles).  d2+EPS lies in [1e-4, ~1e5], so the product neither under- nor overflows.
+// Used for a fraction of the quads to balance the two pipes.
+__device__ __forceinline__ void pair4_shared_rcp(const float4 X, const float4 Y, const float4 M, const float2 nxi,
+                                                 const float2 nyi, float2& ax, float2& ay) {
+    const float2 dxa = __fadd2_rn(make_float2(X.x, X.y), nxi), dxb = __fadd2_rn(make_float2(X.z, X.w), nxi);
+    const float2 dya = __fadd2_rn(make_float2(Y.x, Y.y), nyi), dyb = __fadd2_rn(make_float2(Y.z, Y.w), nyi);
+    const float2 A = __ffma2_rn(dya, dya, __ffma2_rn(dxa, dxa, make_float2(kEps, kEps)));
+    const float2 B = __ffma2_rn(dyb, dyb, __ffma2_rn(dxb, dxb, make_float2(kEps, kEps)));
+    const float2 P = __fmul2_rn(A, B);
+    const float2 R = make_float2(rcp_approx(P.x), rcp_approx(P.y));
+    const float2 sa = __fmul2_rn(make_float2(M.x, M.y), __fmul2_rn(R, B));
+    const float2 sb = __fmul2_rn(make_float2(M.z, M.w), __fmul2_rn(R, A));
+    ax = __ffma2_rn(sa, dxa, ax); ay = __ffma2_rn(sa, dya, ay);
+    ax = __ffma2_rn(sb, dxb, ax); ay = __ffma2_rn(sb, dyb, ay);
+}
+
 // Spin until rank g has published step >= want (P2P_DIRECT ordering).  Bounded: a dead peer must not
 // hang the GPU (a hung box is a lost box) -- after ~4 s we trap.
 __device__ __forceinline__ void wait_flag(const uint32_t* flags, int g, uint32_t want) {
@@ -68,7 +87,7 @@ __device__ __forceinline__ void wait_flag(const uint32_t* flags, int g, uint32_t
     __threadfence_system();
 }
 
-template <int I, int MINB>
+template <int I, int MINB, int SHARE>
 __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const AllPairsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
@@ -156,8 +175,13 @@ __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const All
                 const float4 X = px[q4], Y = py[q4], M = pm[q4];  // broadcast LDS.128
 #pragma unroll
                 for (int k = 0; k < I; k++) {
-                    pair2(X.x, X.y, Y.x, Y.y, M.x, M.y, nxi[k], nyi[k], ax[k], ay[k]);
-                    pair2(X.z, X.w, Y.z, Y.w, M.z, M.w, nxi[k], nyi[k], ax[k], ay[k]);
+                    // SHARE: 0 = one MUFU.RCP per pair; 2 = every quad shares reciprocals; 1 = every other quad
+                    if (SHARE == 2 || (SHARE == 1 && (q4 & 1))) {
+                        pair4_shared_rcp(X, Y, M, nxi[k], nyi[k], ax[k], ay[k]);
+                    } else {
+                        pair2(X.x, X.y, Y.x, Y.y, M.x, M.y, nxi[k], nyi[k], ax[k], ay[k]);
+                        pair2(X.z, X.w, Y.z, Y.w, M.z, M.w, nxi[k], nyi[k], ax[k], ay[k]);
+                    }
                 }
             }
             __syncwarp();
@@ -224,9 +248,9 @@ static int pick_bodies_per_thread(const Engine& e) {
 static int pick_ctas_per_sm(const Engine& e, int I) {
     int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I == 1 ? 5 : (I == 2 ? 4 : 2));  // measured best, profiles/
     // clamp to the instantiated variants
-    if (I == 1) c = c < 3 ? 3 : (c > 5 ? 5 : c);
-    else if (I == 4) c = c < 1 ? 1 : (c > 3 ? 3 : c);
-    else c = c < 2 ? 2 : (c > 4 ? 4 : c);
+    if (I == 1) c = c < 4 ? 4 : (c > 5 ? 5 : c);
+    else if (I == 4) c = c < 2 ? 2 : (c > 3 ? 3 : c);
+    else c = c < 3 ? 3 : (c > 4 ? 4 : c);
     return c;
 }
 
@@ -263,11 +287,11 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     a.partial = e.partial;
 }
 
-template <int I, int MINB>
+template <int I, int MINB, int SHARE>
 static void launch_fast_t(Engine& e, const AllPairsArgs& a) {
     static bool attr_set = false;
     if (!attr_set) {
-        NB_CUDA(cudaFuncSetAttribute(allpairs_fast_kernel<I, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NB_CUDA(cudaFuncSetAttribute(allpairs_fast_kernel<I, MINB, SHARE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(sizeof(FastSmem))));
         attr_set = true;
     }
@@ -277,28 +301,33 @@ static void launch_fast_t(Engine& e, const AllPairsArgs& a) {
     if (n_items == 0) return;
     int grid = e.num_sms * MINB;
     if (grid > n_items) grid = n_items;
-    allpairs_fast_kernel<I, MINB><<<grid, kThreads, sizeof(FastSmem), e.stream>>>(a);
+    allpairs_fast_kernel<I, MINB, SHARE><<<grid, kThreads, sizeof(FastSmem), e.stream>>>(a);
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
+}
+
+template <int SHARE>
+static void launch_fast_s(Engine& e, const AllPairsArgs& a, int I, int C) {
+    // (bodies per thread, resident CTAs per SM) variants; the register budget follows from MINB
+    if (I == 1) {
+        if (C <= 4) launch_fast_t<1, 4, SHARE>(e, a);
+        else launch_fast_t<1, 5, SHARE>(e, a);
+    } else if (I == 4) {
+        if (C <= 2) launch_fast_t<4, 2, SHARE>(e, a);
+        else launch_fast_t<4, 3, SHARE>(e, a);
+    } else {
+        if (C <= 3) launch_fast_t<2, 3, SHARE>(e, a);
+        else launch_fast_t<2, 4, SHARE>(e, a);
+    }
 }
 
 void launch_allpairs_fast(Engine& e, const AllPairsArgs& a) {
     const int I = pick_bodies_per_thread(e);
     const int C = pick_ctas_per_sm(e, I);
-    // (bodies per thread, resident CTAs per SM) variants; the register budget follows from MINB
-    if (I == 1) {
-        if (C <= 3) launch_fast_t<1, 3>(e, a);
-        else if (C == 4) launch_fast_t<1, 4>(e, a);
-        else launch_fast_t<1, 5>(e, a);
-    } else if (I == 4) {
-        if (C <= 1) launch_fast_t<4, 1>(e, a);
-        else if (C == 2) launch_fast_t<4, 2>(e, a);
-        else launch_fast_t<4, 3>(e, a);
-    } else {
-        if (C <= 2) launch_fast_t<2, 2>(e, a);
-        else if (C == 3) launch_fast_t<2, 3>(e, a);
-        else launch_fast_t<2, 4>(e, a);
-    }
+    const int share = e.tune.share_rcp >= 0 ? e.tune.share_rcp : kDefaultShare;
+    if (share == 0) launch_fast_s<0>(e, a, I, C);
+    else if (share == 1) launch_fast_s<1>(e, a, I, C);
+    else launch_fast_s<2>(e, a, I, C);
     e.ctr.allpairs_pairs += static_cast<uint64_t>(a.n_local) * static_cast<uint64_t>(a.n_total > 0 ? a.n_total - 1 : 0);
 }
 

@@ -85,6 +85,7 @@ struct Tuning {
     int bodies_per_thread = 0;  // 0 = auto
     int target_waves = 0;
     int ctas_per_sm = 0;
+    int share_rcp = -1;         // -1 = library default
 };
 
 struct Engine {

@@ -17,8 +17,10 @@ st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 lib.set_stream(st.cuda_stream)
 lib.set_particles(ic.plummer_2d(n, seed=3))
-for bpt, cps in [(1, 3), (1, 4), (1, 5), (2, 2), (2, 3), (2, 4), (4, 2), (4, 3)]:
-    for waves in (16, 64, 128):
+for share in (0, 1, 2):
+  os.environ["NB_SHARE_RCP"] = str(share)
+  for bpt, cps in [(1, 5), (2, 3), (2, 4), (4, 2), (4, 3)]:
+    for waves in (64,):
         lib.tune(bpt, waves, cps)
         for _ in range(2):
             lib.step_brute_force(0.01)
@@ -31,5 +33,5 @@ for bpt, cps in [(1, 3), (1, 4), (1, 5), (2, 2), (2, 3), (2, 4), (4, 2), (4, 3)]
         e1.record(st)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        print(json.dumps({"n": n, "bodies_per_thread": bpt, "ctas_per_sm": cps, "waves": waves, "ms": ms,
+        print(json.dumps({"n": n, "share_rcp": share, "bodies_per_thread": bpt, "ctas_per_sm": cps, "waves": waves, "ms": ms,
                           "pairs_per_s": n * (n - 1) / (ms * 1e-3), "frac_fp32": n * (n - 1) * 12 / (ms * 1e-3) / 74.45e12}), flush=True)
