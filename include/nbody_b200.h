@@ -115,6 +115,11 @@ void nbx_get_counters(nbx_counters *out);
 void nbx_reset_counters(void);
 int32_t nbx_bh_count_interactions(int32_t enable);
 
+/* Domain partitioning of the FAST Barnes-Hut step: 0 = automatic (one part per GPU when
+ * sharded over several GPUs and the set has >= 65,536 bodies; one tree otherwise), 1 = always one replicated
+ * tree, 2..8 on a single GPU = that many "virtual ranks" (exercises the partitioned code path for tests). */
+int32_t nbx_bh_partition(int32_t parts);
+
 /* Device time (ms, CUDA events on the library stream) of the phases of the most recent step:
  * [0] all-pairs / traversal kernel  [1] integrate  [2] aabb  [3] keys  [4] sort  [5] tree build
  * [6] centre-of-mass  [7] cross-rank wait/gather.  Only recorded when enabled (adds event overhead). */
@@ -131,7 +136,7 @@ int32_t nbx_bh_accelerations(float theta, float *axy_out, int32_t n);
 /* ---- multi-GPU (one process per GPU; particles shard by index) -------------
  * Wiring is done by the host framework's process group (torch.distributed in this repo):
  *   1. every rank: nbx_dist_init(rank, world, max_particles) -> allocates the symmetric arena
- *   2. every rank: nbx_dist_export(handle)  ; all-gather the 64-byte handles ; nbx_dist_import(all)
+ *   2. every rank: nbx_dist_export(handle)  ; all-gather the nbx_dist_handle_bytes()-byte handles ; nbx_dist_import(all)
  *   3. (NCCL transport only) rank 0: nbx_dist_nccl_unique_id ; broadcast ; all: nbx_dist_nccl_init
  * After that nb_set_particles / nb_step_* / nb_get_particles are collective calls.
  */

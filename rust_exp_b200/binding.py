@@ -40,6 +40,7 @@ SYMBOLS = {
     "nbx_get_counters": (None, [vp]),
     "nbx_reset_counters": (None, []),
     "nbx_bh_count_interactions": (i32, [i32]),
+    "nbx_bh_partition": (i32, [i32]),
     "nbx_phase_timing": (i32, [i32]),
     "nbx_get_phase_ms": (i32, [vp]),
     "nbx_accelerations": (i32, [vp, i32]),
@@ -171,6 +172,9 @@ class NBodyLib:
 
     def bh_count_interactions(self, on: bool) -> None:
         self.L.nbx_bh_count_interactions(1 if on else 0)
+
+    def bh_partition(self, parts: int) -> None:
+        self._chk(self.L.nbx_bh_partition(parts), "nbx_bh_partition")
 
     def phase_timing(self, on: bool) -> None:
         self.L.nbx_phase_timing(1 if on else 0)

@@ -118,6 +118,8 @@ void nbx_shutdown(void) {
     dist_shutdown(e);
     bh_shutdown(e);
     if (e.arena.base) cudaFree(e.arena.base);
+    if (e.bh_arena) cudaFree(e.bh_arena);
+    e.bh_arena = nullptr;
     if (e.mirror) cudaFree(e.mirror);
     if (e.partial) cudaFree(e.partial);
     if (e.force) cudaFree(e.force);
@@ -216,6 +218,16 @@ int32_t nbx_bh_count_interactions(int32_t enable) {
     return 0;
 }
 
+int32_t nbx_bh_partition(int32_t parts) {
+    NB_LOCK();
+    if (parts < 0 || parts > kMaxRanks) {
+        set_error("parts must be 0..%d", kMaxRanks);
+        return -1;
+    }
+    engine().bh_partition = parts;
+    return 0;
+}
+
 int32_t nbx_phase_timing(int32_t enable) {
     NB_LOCK();
     Engine& e = engine();
@@ -272,7 +284,7 @@ int32_t nbx_dist_init(int32_t rank, int32_t world, int32_t max_particles) {
     ensure_init(e);
     return dist_init(e, rank, world, max_particles);
 }
-int32_t nbx_dist_handle_bytes(void) { return 64; }
+int32_t nbx_dist_handle_bytes(void) { return 128; }
 int32_t nbx_dist_export(void* handle_out) {
     NB_LOCK();
     return dist_export(engine(), handle_out);

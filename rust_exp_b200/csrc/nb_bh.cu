@@ -30,6 +30,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <vector>
 #include <cstring>
 
 #include "nb_engine.h"
@@ -51,9 +52,56 @@ struct BhStatus {
     int aabb_enc[4];          // ordered-int encodings of x1,y1 (min) and x2,y2 (max)
     int n_mine;
     int n_interior;
+    int n_deep;               // partitioned build: interior nodes at or below the cut level
+    int n_top;                // partitioned build: interior nodes of the shared top tree
     unsigned long long interactions;
     unsigned long long visited;
 };
+
+constexpr int kCutLevel = 5;
+constexpr int kNumCells = 1 << (2 * kCutLevel);          // 1024
+constexpr int kTopNodes = (kNumCells * 4 - 1) / 3;       // levels 0..kCutLevel: 1365
+constexpr int kPartShift = 22;                           // 4M blocks per part
+constexpr int kCellShift = 2 * (kLevels - kCutLevel);
+
+struct __align__(16) CellEntry {
+    double M, MX, MY;
+    int count;
+    int child;        // global block index of the cell's child block (interior cell), else -1
+    float x, y, m;    // leaf record (single body, or merged group)
+    int pad;
+};
+
+struct PartBufs {
+    int cap = 0;                                   // body capacity of this part
+    int n = 0;                                     // bodies of this part this step (host copy)
+    int *sel = nullptr, *idx_sorted = nullptr;
+    unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+    float *sx = nullptr, *sy = nullptr, *sm = nullptr;
+    double *w3 = nullptr, *p3 = nullptr, *tile_sums = nullptr;
+    signed char *delta = nullptr, *dcap = nullptr;
+    unsigned char* close = nullptr;
+    int *count = nullptr, *base = nullptr, *owner = nullptr;
+    int cap_blocks = 0;
+    float4* nblk = nullptr;       // in the BH arena when real ranks are used (peer-visible)
+    int4* ncblk = nullptr;
+    CellEntry* celltab = nullptr;
+    bool arena_owned = false;     // nblk/ncblk/celltab point into the IPC arena
+    BhStatus* status = nullptr;   // per part (n_deep, interactions, ...)
+};
+
+struct TopBufs {
+    int* tcount = nullptr;
+    double* tm3 = nullptr;        // [3][kTopNodes]
+    float4* tleaf = nullptr;      // x, y, m, (unused)
+    int* tchild = nullptr;        // level-kCutLevel nodes: child block or -1
+    float4* blk = nullptr;        // top blocks: 1 + (kTopNodes - kNumCells) blocks
+    int4* cblk = nullptr;
+    int* hist = nullptr;          // [kNumCells]
+    int* hist_host = nullptr;     // pinned
+};
+
+struct PeerU32 { uint32_t* p[kMaxRanks]; };
 
 struct BhWork {
     int cap_n = 0;
@@ -81,6 +129,12 @@ struct BhWork {
     bool warned = false;
     bool status_pending = false;
     cudaEvent_t status_ev = nullptr;
+    // domain-partitioned mode
+    std::vector<PartBufs> parts;
+    TopBufs top;
+    uint32_t bh_epoch = 0;
+    float2* acc_src = nullptr;       // where this step's per-local-body accelerations ended up
+    bool last_partitioned = false;
 };
 
 static BhWork& work(Engine& e) {
@@ -106,6 +160,8 @@ __global__ void bh_reset_kernel(BhStatus* st) {
         st->aabb_enc[2] = st->aabb_enc[3] = f2ord(-3.40282347e+38f);
         st->interactions = 0;
         st->visited = 0;
+        st->n_deep = 0;
+        st->n_top = 0;
     }
 }
 
@@ -313,6 +369,8 @@ struct BuildArgs {
     float4* nblk;     // block-SoA node records: block b = {x[4], y[4], m[4], s[4]} at nblk[4b .. 4b+3]
     int4* ncblk;      // child block index of each of the 4 nodes of block b (-1 = leaf)
     int n, cap_interior;
+    unsigned part_off;   // added to every child block index (global block index space of partitioned trees)
+    int cut_level;       // partitioned build: interior nodes at levels >= cut_level are counted in n_deep
 };
 
 __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
@@ -329,6 +387,10 @@ __global__ void bh_owner_kernel(const BuildArgs a, int* __restrict__ owner, BhSt
     const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
     const int b = a.base[i];
     for (int k = 0; k < dhi - dlo && b + k < a.cap_interior; k++) owner[b + k] = i;
+    if (a.cut_level > 0) {
+        const int deep = dhi - max(dlo, a.cut_level - 1);
+        if (deep > 0) atomicAdd(&st->n_deep, deep);
+    }
     if (i == 0) {
         const int total = a.base[a.n - 1];   // count[n-1] == 0
         st->node_count = 1 + 4 * min(total, a.cap_interior);
@@ -394,7 +456,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
             a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
             a.nblk[2] = make_float4(static_cast<float>(M), 0.f, 0.f, 0.f);
             a.nblk[3] = make_float4(__fsub_rn(x2, x1), -1.f, -1.f, -1.f);
-            a.ncblk[0] = make_int4(blk, -1, -1, -1);
+            a.ncblk[0] = make_int4(static_cast<int>(a.part_off) + blk, -1, -1, -1);
         }
         float4 rec[4];
         int4 ch = make_int4(-1, -1, -1, -1);
@@ -418,7 +480,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                     // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
                     rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
-                    chp[q] = 1 + cid;
+                    chp[q] = static_cast<int>(a.part_off) + 1 + cid;
                 } else {
                     float bx = 0.f, by = 0.f, bm = 0.f;
                     for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
@@ -511,11 +573,23 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 // child to be opened; only children that some lane must open are pushed, with that lane mask.  Every body
 // therefore evaluates exactly the reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and
 // the body's own leaf (d = 0, :365) need no test: their contribution is an exact zero because EPS > 0.
+// Block index space: (part << shift) | block.  One tree: shift = 31, part 0.  Partitioned trees: part g < world
+// is rank g's subtree forest (possibly in a PEER GPU's memory, walked in place over NVLink), part kMaxRanks is
+// the small shared top tree.  Accelerations are scattered to the rank that owns the body's index shard.
+struct TreeTable {
+    const float4* blk[kMaxRanks + 1];
+    const int4* cblk[kMaxRanks + 1];
+    float2* acc[kMaxRanks];
+    int shift;
+    unsigned root;
+    int shard_len;     // L: owner of body i is i / L, its slot i % L
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
-    const float4* __restrict__ nblk, const int4* __restrict__ ncblk, const float* __restrict__ sx,
+    const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
-    int i_begin, float theta2, float2* __restrict__ acc, BhStatus* st) {
+    float theta2, BhStatus* st) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = blockIdx.x * kTravWarps + warp;
@@ -532,7 +606,7 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     unsigned long long n_int = 0, n_vis = 0;
     {
         const unsigned m0 = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) s[0] = make_uint2(0u, m0);   // block 0 = {root, empty, empty, empty}
+        if (lane == 0) s[0] = make_uint2(tt.root, m0);   // root block = {root, empty, empty, empty}
         sp = 1;
         __syncwarp();
         if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
@@ -542,8 +616,9 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
         const uint2 e = s[sp];
         __syncwarp();
         const bool act = (e.y >> lane) & 1u;
-        const float4 X = __ldg(&nblk[4 * e.x + 0]), Y = __ldg(&nblk[4 * e.x + 1]);
-        const float4 M = __ldg(&nblk[4 * e.x + 2]), S = __ldg(&nblk[4 * e.x + 3]);
+        const unsigned part = e.x >> tt.shift, bi = e.x & ((1u << tt.shift) - 1u);
+        const float4* __restrict__ nb4 = tt.blk[part] + 4 * static_cast<size_t>(bi);
+        const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), S = __ldg(nb4 + 3);
         const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
         const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
         const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
@@ -571,7 +646,7 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
         }
         const unsigned any = __reduce_or_sync(0xffffffffu, ob);
         if (any) {
-            const int4 C = __ldg(&ncblk[e.x]);
+            const int4 C = __ldg(tt.cblk[part] + bi);
             // push order 3..0 so that child 0 is opened first (DFS-like order)
             if (any & 8u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 8u); if (lane == 0) s[sp] = make_uint2(C.w, om); sp++; }
             if (any & 4u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 4u); if (lane == 0) s[sp] = make_uint2(C.z, om); sp++; }
@@ -580,7 +655,11 @@ __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
         }
         __syncwarp();
     }
-    if (live) acc[idx_sorted[pos] - i_begin] = make_float2(ax.x + ax.y, ay.x + ay.y);
+    if (live) {
+        const int gi = idx_sorted[pos];
+        const int own = gi / tt.shard_len;
+        tt.acc[own][gi - own * tt.shard_len] = make_float2(ax.x + ax.y, ay.x + ay.y);
+    }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
             n_int += __shfl_xor_sync(0xffffffffu, n_int, o);
@@ -663,6 +742,35 @@ struct InRange {
 using Iota = thrust::counting_iterator<int>;
 
 static void check_status(Engine& e, struct BhWork& w, bool sync_now);
+static void bh_forces_partitioned(Engine& e, float theta, int nparts);
+
+// How many domain parts the FAST Barnes-Hut step uses: the world size when sharded over real GPUs (and the
+// set is large enough for a level-5 cut to make sense), NB_BH_PARTS virtual parts on one GPU (testing), else 1.
+static int bh_partition_count(const Engine& e) {
+    if (e.mode != NBX_MODE_FAST) return 1;
+    int min_n = 65536;
+    if (const char* s = getenv("NB_BH_PARTS_MIN_N")) min_n = atoi(s);
+    if (e.n < min_n) return 1;
+    if (e.dist && e.world > 1) {
+        if (e.bh_partition == 1 || e.bh_arena == nullptr) return 1;
+        return e.world;
+    }
+    int parts = e.bh_partition;
+    if (parts <= 0) { if (const char* s = getenv("NB_BH_PARTS")) parts = atoi(s); }
+    if (parts > kMaxRanks) parts = kMaxRanks;
+    return parts > 1 ? parts : 1;
+}
+
+static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, const float* sy, const int* idx_sorted,
+                            const int* mine, int n_list, float theta, BhStatus* st) {
+    const int blocks = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
+    if (e.bh_count)
+        bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, theta * theta, st);
+    else
+        bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, theta * theta, st);
+    NB_CUDA(cudaGetLastError());
+    e.ctr.kernel_launches++;
+}
 
 // ---- host orchestration ----------------------------------------------------------------------------------------
 static void ensure_work(Engine& e, BhWork& w, int n) {
@@ -728,6 +836,16 @@ static void bh_forces(Engine& e, float theta) {
         NB_CUDA(cudaMalloc(&w.acc, sizeof(float2) * static_cast<size_t>(e.lay.L)));
         w.cap_acc = static_cast<int>(e.lay.L);
     }
+    w.acc_src = w.acc;
+    w.last_partitioned = false;
+    const int nparts = bh_partition_count(e);
+    if (nparts > 1) {
+        bh_forces_partitioned(e, theta, nparts);
+        NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, e.stream));
+        NB_CUDA(cudaEventRecord(w.status_ev, e.stream));
+        w.status_pending = true;
+        return;
+    }
     // sharded: slot index == body index only while every shard but the last is full (L-aligned shards)
     const GlobalPos gp = global_positions(e);
     cudaStream_t s = e.stream;
@@ -778,7 +896,7 @@ static void bh_forces(Engine& e, float theta) {
             bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
             size_t tb = w.cub_bytes;
             cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
-            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4};
+            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0};
             bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
             bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
             e.ctr.kernel_launches += 4;
@@ -793,20 +911,420 @@ static void bh_forces(Engine& e, float theta) {
         }
         PhaseScope ps(e, 0);
         if (n_list > 0) {
-            const int blocks = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
-            if (e.bh_count)
-                bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, s>>>(w.nblk, w.ncblk, w.sx, w.sy, w.idx_sorted, mine,
-                                                                                n_list, ib, theta * theta, w.acc, w.status);
-            else
-                bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, s>>>(w.nblk, w.ncblk, w.sx, w.sy, w.idx_sorted, mine,
-                                                                                 n_list, ib, theta * theta, w.acc, w.status);
-            e.ctr.kernel_launches++;
+            // replicated tree: this rank walks the bodies of its own index shard, so every write is local
+            TreeTable tt{};
+            tt.blk[0] = w.nblk; tt.cblk[0] = w.ncblk;
+            for (int g = 0; g < kMaxRanks; g++) tt.acc[g] = w.acc;
+            tt.acc[e.rank] = w.acc;
+            tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
+            launch_traverse(e, tt, w.sx, w.sy, w.idx_sorted, mine, n_list, theta, w.status);
         }
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
     NB_CUDA(cudaEventRecord(w.status_ev, s));
     w.status_pending = true;
+}
+
+// =================================================================================================
+// Domain-partitioned Barnes-Hut (multi-GPU)
+//
+// The replicated tree does not scale: every rank sorts and builds all N bodies.  Here the level-kCutLevel
+// cells of the (global, reference-identical) quadtree are dealt to the ranks as contiguous Morton ranges of
+// ~N/G bodies each -- a space-filling-curve domain split at cell granularity, so that every subtree below
+// the cut belongs to exactly one rank.  A rank selects, sorts and builds ONLY the bodies of its cells
+// (same single-pass build, same global root box => the same cells the reference would make), and publishes
+// one 48-byte entry per cell (count, f64 mass moments, leaf record or child block).  The <= 341 nodes above
+// the cut are rebuilt by every rank from the G published cell tables.  No locally-essential tree is ever
+// materialised or exchanged: block indices carry a part id, and the walk follows a remote subtree IN PLACE
+// in the owning peer's HBM over NVLink -- the opening test decides which remote nodes are touched, which is
+// exactly the LET, fetched on demand.  A rank walks the bodies of its own cells (spatially compact =>
+// mostly local nodes) and scatters each acceleration to the rank that owns the body's index shard.
+// With NB_BH_PARTS=G on ONE GPU the same code runs with G "virtual ranks" (parity-tested on a single GPU).
+// =================================================================================================
+__global__ void __launch_bounds__(256) bh_cell_hist_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ hist) {
+    __shared__ int sh[kNumCells];
+    for (int c = threadIdx.x; c < kNumCells; c += blockDim.x) sh[c] = 0;
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&sh[static_cast<int>(keys[i] >> kCellShift)], 1);
+    __syncthreads();
+    for (int c = threadIdx.x; c < kNumCells; c += blockDim.x)
+        if (sh[c]) atomicAdd(&hist[c], sh[c]);
+}
+
+struct InCells {
+    const unsigned long long* keys;
+    int c0, c1;
+    __device__ bool operator()(int i) const { const int c = static_cast<int>(keys[i] >> kCellShift); return c >= c0 && c < c1; }
+};
+
+__global__ void bh_gather_keys_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ sel, int n,
+                                      unsigned long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = keys[sel[i]];
+}
+
+// one thread per level-kCutLevel cell of this part: publish its entry
+__global__ void bh_celltab_kernel(const BuildArgs a, int c0, int c1, CellEntry* __restrict__ tab) {
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const size_t stride = static_cast<size_t>(a.n) + 1;
+    auto lb = [&](unsigned long long cell) {   // first sorted body whose cell index is >= cell
+        int lo = 0, hi = a.n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((a.keys[mid] >> kCellShift) < cell) lo = mid + 1; else hi = mid; }
+        return lo;
+    };
+    const int first = lb(static_cast<unsigned long long>(c)), end = lb(static_cast<unsigned long long>(c) + 1ull);
+    const int cnt = end - first;
+    CellEntry en;
+    en.M = en.MX = en.MY = 0.0; en.count = cnt; en.child = -1; en.x = en.y = en.m = 0.f; en.pad = 0;
+    if (cnt >= 1) {
+        en.M = a.p3[end] - a.p3[first];
+        en.MX = a.p3[stride + end] - a.p3[stride + first];
+        en.MY = a.p3[2 * stride + end] - a.p3[2 * stride + first];
+    }
+    if (cnt == 1) {
+        en.x = a.sx[first]; en.y = a.sy[first]; en.m = a.sm[first];
+    } else if (cnt >= 2) {
+        int cid = -1;
+        if (static_cast<int>(a.dcap[first]) >= kCutLevel) {
+            cid = interior_id(a, first, kCutLevel);
+            if (cid >= a.cap_interior) cid = -1;
+        }
+        if (cid >= 0) {
+            en.child = static_cast<int>(a.part_off) + 1 + cid;
+        } else {   // the whole cell merges (rs-src/nbody.rs:249-260)
+            float bx = 0.f, by = 0.f, bm = 0.f;
+            for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
+            en.x = bx; en.y = by; en.m = bm;
+        }
+    }
+    tab[c] = en;
+}
+
+struct TopArgs {
+    const CellEntry* tab[kMaxRanks];   // tab[g] valid for cells [cut[g], cut[g+1])
+    int cut[kMaxRanks + 1];
+    int nparts;
+    int* tcount; double* tm3; float4* tleaf; int* tchild;
+    float4* blk; int4* cblk;
+    unsigned top_off;                  // part id of the top tree << kPartShift
+};
+
+__device__ __forceinline__ int top_off_level(int l) { return ((1 << (2 * l)) - 1) / 3; }
+
+// cell width s = x2 - x1 of cell `path` at `level` (rs-src/nbody.rs:286-301 replayed from the root box)
+__device__ __forceinline__ float cell_width(const BhStatus* st, int level, int path) {
+    float x1 = ord2f(st->aabb_enc[0]), x2 = ord2f(st->aabb_enc[2]);
+    for (int t = 0; t < level; t++) {
+        const int q = (path >> (2 * (level - 1 - t))) & 3;
+        const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f);
+        if (q & 1) x1 = cx; else x2 = cx;
+    }
+    return __fsub_rn(x2, x1);
+}
+
+// one block: rebuild the nodes above the cut from the published cell tables (identical on every rank)
+__global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhStatus* st) {
+    const int tid = threadIdx.x;
+    const int offk = top_off_level(kCutLevel);
+    for (int c = tid; c < kNumCells; c += blockDim.x) {
+        int g = 0;
+        while (g + 1 < a.nparts && c >= a.cut[g + 1]) g++;
+        const CellEntry en = a.tab[g][c];
+        a.tcount[offk + c] = en.count;
+        a.tm3[offk + c] = en.M; a.tm3[kTopNodes + offk + c] = en.MX; a.tm3[2 * kTopNodes + offk + c] = en.MY;
+        a.tleaf[offk + c] = make_float4(en.x, en.y, en.m, 0.f);
+        a.tchild[offk + c] = en.child;
+    }
+    __syncthreads();
+    __shared__ int s_top;
+    if (tid == 0) s_top = 0;
+    for (int l = kCutLevel - 1; l >= 0; l--) {
+        const int off = top_off_level(l), offc = top_off_level(l + 1);
+        for (int p = tid; p < (1 << (2 * l)); p += blockDim.x) {
+            int cnt = 0; double M = 0.0, MX = 0.0, MY = 0.0; float4 leaf = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; q++) {
+                const int ch = offc + 4 * p + q;
+                const int cc = a.tcount[ch];
+                cnt += cc; M += a.tm3[ch]; MX += a.tm3[kTopNodes + ch]; MY += a.tm3[2 * kTopNodes + ch];
+                if (cc == 1) leaf = a.tleaf[ch];
+            }
+            a.tcount[off + p] = cnt;
+            a.tm3[off + p] = M; a.tm3[kTopNodes + off + p] = MX; a.tm3[2 * kTopNodes + off + p] = MY;
+            a.tleaf[off + p] = leaf;
+            a.tchild[off + p] = -1;
+            if (cnt >= 2) atomicAdd(&s_top, 1);
+        }
+        __syncthreads();
+    }
+    auto record = [&](int level, int path, float4& rec, int& child) {
+        const int node = top_off_level(level) + path;
+        const int cnt = a.tcount[node];
+        rec = make_float4(0.f, 0.f, 0.f, -1.0f);
+        child = -1;
+        if (cnt == 0) return;
+        const float4 lf = a.tleaf[node];
+        if (cnt == 1) { rec = make_float4(lf.x, lf.y, lf.z, -1.0f); return; }
+        int ch = -1;
+        if (level == kCutLevel) ch = a.tchild[node];
+        else ch = static_cast<int>(a.top_off) + 1 + node;   // top block of an interior top node
+        if (ch < 0) { rec = make_float4(lf.x, lf.y, lf.z, -1.0f); return; }   // merged cell at the cut level
+        const double M = a.tm3[node];
+        rec = make_float4(static_cast<float>(a.tm3[kTopNodes + node] / M), static_cast<float>(a.tm3[2 * kTopNodes + node] / M),
+                          static_cast<float>(M), cell_width(st, level, path));
+        child = ch;
+    };
+    // block 0: {root, empty, empty, empty}; block 1 + node: the four children of interior top node `node`
+    if (tid == 0) {
+        float4 r; int ch;
+        record(0, 0, r, ch);
+        a.blk[0] = make_float4(r.x, 0.f, 0.f, 0.f); a.blk[1] = make_float4(r.y, 0.f, 0.f, 0.f);
+        a.blk[2] = make_float4(r.z, 0.f, 0.f, 0.f); a.blk[3] = make_float4(r.w, -1.f, -1.f, -1.f);
+        a.cblk[0] = make_int4(ch, -1, -1, -1);
+        st->n_top = s_top;
+    }
+    for (int l = 0; l < kCutLevel; l++) {
+        for (int p = tid; p < (1 << (2 * l)); p += blockDim.x) {
+            const int node = top_off_level(l) + p;
+            float4 r[4]; int ch[4];
+            for (int q = 0; q < 4; q++) record(l + 1, 4 * p + q, r[q], ch[q]);
+            const int b = 1 + node;
+            a.blk[4 * b + 0] = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
+            a.blk[4 * b + 1] = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
+            a.blk[4 * b + 2] = make_float4(r[0].z, r[1].z, r[2].z, r[3].z);
+            a.blk[4 * b + 3] = make_float4(r[0].w, r[1].w, r[2].w, r[3].w);
+            a.cblk[b] = make_int4(ch[0], ch[1], ch[2], ch[3]);
+        }
+    }
+}
+
+// ---- partitioned step: host side -------------------------------------------------------------------------
+__global__ void bh_flag_signal_kernel(PeerU32 peers, int world, int slot, uint32_t value) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peers.p[g] + slot) = value;
+        __threadfence_system();
+    }
+}
+__global__ void bh_flag_wait_kernel(const uint32_t* flags, int world, uint32_t want) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        const volatile uint32_t* f = flags + g;
+        const long long t0 = clock64();
+        while (static_cast<int32_t>(*f - want) < 0) {
+            __nanosleep(200);
+            if (clock64() - t0 > 8000000000LL) {   // ~4 s: a dead peer must not hang this GPU
+                printf("nbody_b200: timeout waiting for rank %d (Barnes-Hut epoch %u, at %u)\n", g, want, *f);
+                __trap();
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+static void part_ensure(Engine& e, BhWork& w, PartBufs& P, int n, bool in_arena) {
+    if (n <= P.cap) return;
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    auto fr = [](void* p) { if (p) cudaFree(p); };
+    fr(P.sel); fr(P.idx_sorted); fr(P.keys); fr(P.keys_sorted); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.w3); fr(P.p3);
+    fr(P.tile_sums); fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner);
+    const size_t N = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 1024;   // headroom: partitions drift
+    NB_CUDA(cudaMalloc(&P.sel, N * 4)); NB_CUDA(cudaMalloc(&P.idx_sorted, N * 4));
+    NB_CUDA(cudaMalloc(&P.keys, N * 8)); NB_CUDA(cudaMalloc(&P.keys_sorted, N * 8));
+    NB_CUDA(cudaMalloc(&P.sx, N * 4)); NB_CUDA(cudaMalloc(&P.sy, N * 4)); NB_CUDA(cudaMalloc(&P.sm, N * 4));
+    NB_CUDA(cudaMalloc(&P.w3, 3 * (N + 1) * 8)); NB_CUDA(cudaMalloc(&P.p3, 3 * (N + 1) * 8));
+    NB_CUDA(cudaMalloc(&P.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
+    NB_CUDA(cudaMalloc(&P.delta, N)); NB_CUDA(cudaMalloc(&P.dcap, N)); NB_CUDA(cudaMalloc(&P.close, N));
+    NB_CUDA(cudaMalloc(&P.count, N * 4)); NB_CUDA(cudaMalloc(&P.base, N * 4));
+    if (!in_arena) {
+        fr(P.nblk); fr(P.ncblk); fr(P.celltab);
+        P.cap_blocks = static_cast<int>(std::min<size_t>(2 * N + 4096, (1u << kPartShift) - 1));
+        NB_CUDA(cudaMalloc(&P.nblk, sizeof(float4) * 4 * static_cast<size_t>(P.cap_blocks)));
+        NB_CUDA(cudaMalloc(&P.ncblk, sizeof(int4) * static_cast<size_t>(P.cap_blocks)));
+        NB_CUDA(cudaMalloc(&P.celltab, sizeof(CellEntry) * kNumCells));
+    }
+    NB_CUDA(cudaMalloc(&P.owner, sizeof(int) * static_cast<size_t>(P.cap_blocks)));
+    P.cap = static_cast<int>(N);
+    (void)w;
+}
+
+static void top_ensure(TopBufs& t) {
+    if (t.blk) return;
+    NB_CUDA(cudaMalloc(&t.tcount, sizeof(int) * kTopNodes));
+    NB_CUDA(cudaMalloc(&t.tm3, sizeof(double) * 3 * kTopNodes));
+    NB_CUDA(cudaMalloc(&t.tleaf, sizeof(float4) * kTopNodes));
+    NB_CUDA(cudaMalloc(&t.tchild, sizeof(int) * kTopNodes));
+    NB_CUDA(cudaMalloc(&t.blk, sizeof(float4) * 4 * (kTopNodes + 1)));
+    NB_CUDA(cudaMalloc(&t.cblk, sizeof(int4) * (kTopNodes + 1)));
+    NB_CUDA(cudaMalloc(&t.hist, sizeof(int) * kNumCells));
+    NB_CUDA(cudaMallocHost(&t.hist_host, sizeof(int) * kNumCells));
+}
+
+// sort + build the subtree forest of one part (bodies whose level-kCutLevel cell lies in [c0, c1))
+static void build_part(Engine& e, BhWork& w, PartBufs& P, const GlobalPos& gp, int n_all, int c0, int c1, int part_id) {
+    cudaStream_t s = e.stream;
+    const int T = 256;
+    const int n = P.n;
+    if (n > 0) {
+        size_t tb = w.cub_bytes;
+        cub::DeviceSelect::If(w.cub_tmp, tb, Iota(0), P.sel, &w.status->n_mine, n_all, InCells{w.keys, c0, c1}, s);
+        const int G = (n + T - 1) / T;
+        bh_gather_keys_kernel<<<G, T, 0, s>>>(w.keys, P.sel, n, P.keys);
+        tb = w.cub_bytes;
+        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, P.keys, P.keys_sorted, P.sel, P.idx_sorted, n, 0, kKeyBits, s);
+        bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, P.idx_sorted, n, P.sx, P.sy, P.sm, P.w3);
+        const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
+        const size_t stride = static_cast<size_t>(n) + 1;
+        scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(P.w3, len, stride, P.tile_sums, ntiles);
+        scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(P.tile_sums, ntiles);
+        scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(P.w3, P.p3, len, stride, P.tile_sums, ntiles);
+        bh_delta_kernel<<<G, T, 0, s>>>(P.keys_sorted, P.sx, P.sy, n, P.delta, P.close);
+        bh_cap_kernel<<<G, T, 0, s>>>(P.delta, P.close, n, P.dcap, P.count);
+        tb = w.cub_bytes;
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, P.count, P.base, n, s);
+        e.ctr.kernel_launches += 8;
+    }
+    BuildArgs ba{P.keys_sorted, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, P.nblk, P.ncblk, n, P.cap_blocks - 2,
+                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel};
+    if (n > 0) {
+        const int G = (n + T - 1) / T;
+        bh_owner_kernel<<<G, T, 0, s>>>(ba, P.owner, w.status);
+        bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, P.owner, w.status);
+        e.ctr.kernel_launches += 2;
+    }
+    if (c1 > c0) {
+        bh_celltab_kernel<<<(c1 - c0 + 127) / 128, 128, 0, s>>>(ba, c0, c1, P.celltab);
+        e.ctr.kernel_launches++;
+    }
+    NB_CUDA(cudaGetLastError());
+}
+
+static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
+    BhWork& w = work(e);
+    const bool real = e.dist && e.world > 1;      // real ranks: this process builds part e.rank only
+    const int n = e.n;
+    const int nl = local_count(e);
+    const GlobalPos gp = global_positions(e);     // sharded: gathers all positions first (epoch-ordered)
+    cudaStream_t s = e.stream;
+    const int T = 256, G = (n + T - 1) / T;
+    top_ensure(w.top);
+    {
+        PhaseScope ps(e, 2);
+        bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
+        bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
+        e.ctr.kernel_launches += 2;
+    }
+    {
+        PhaseScope ps(e, 3);
+        bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
+        NB_CUDA(cudaMemsetAsync(w.top.hist, 0, sizeof(int) * kNumCells, s));
+        bh_cell_hist_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(w.keys, n, w.top.hist);
+        e.ctr.kernel_launches += 2;
+        // the only host round trip of the step: 4 KB of cell counts -> the partition (identical on all ranks)
+        NB_CUDA(cudaMemcpyAsync(w.top.hist_host, w.top.hist, sizeof(int) * kNumCells, cudaMemcpyDeviceToHost, s));
+        NB_CUDA(cudaStreamSynchronize(s));
+    }
+    int cut[kMaxRanks + 1], cnt[kMaxRanks];
+    {
+        long long cum = 0;
+        int g = 1;
+        cut[0] = 0;
+        for (int c = 0; c < kNumCells; c++) {
+            while (g < nparts && cum * nparts >= static_cast<long long>(g) * n) cut[g++] = c;
+            cum += w.top.hist_host[c];
+        }
+        while (g <= nparts) cut[g++] = kNumCells;
+        for (int r = 0; r < nparts; r++) {
+            long long c2 = 0;
+            for (int c = cut[r]; c < cut[r + 1]; c++) c2 += w.top.hist_host[c];
+            cnt[r] = static_cast<int>(c2);
+        }
+    }
+    if (static_cast<int>(w.parts.size()) != (real ? 1 : nparts)) w.parts.resize(real ? 1 : nparts);
+    const uint32_t epoch = ++w.bh_epoch;
+    {
+        PhaseScope ps(e, 5);
+        for (int r = 0; r < nparts; r++) {
+            if (real && r != e.rank) continue;
+            PartBufs& P = w.parts[real ? 0 : r];
+            if (real && !P.arena_owned) {
+                P.nblk = reinterpret_cast<float4*>(e.bh_arena + e.bh_lay.off_nblk);
+                P.ncblk = reinterpret_cast<int4*>(e.bh_arena + e.bh_lay.off_ncblk);
+                P.celltab = reinterpret_cast<CellEntry*>(e.bh_arena + e.bh_lay.off_celltab);
+                P.cap_blocks = e.bh_lay.cap_blocks;
+                P.arena_owned = true;
+            }
+            part_ensure(e, w, P, std::max(cnt[r], 1), real);
+            P.n = cnt[r];
+            build_part(e, w, P, gp, n, cut[r], cut[r + 1], r);
+        }
+    }
+    TopArgs ta{};
+    TreeTable tt{};
+    tt.shift = kPartShift;
+    tt.root = static_cast<unsigned>(kMaxRanks) << kPartShift;
+    tt.shard_len = static_cast<int>(e.lay.L);
+    for (int r = 0; r <= nparts; r++) ta.cut[r] = cut[r];
+    ta.nparts = nparts;
+    if (real) {
+        PhaseScope ps(e, 7);
+        // publish "my subtrees and cell table are ready", then wait for everybody's
+        PeerU32 pf{};
+        for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags);
+        bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
+        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags), e.world, epoch);
+        e.ctr.kernel_launches += 2;
+        for (int g = 0; g < e.world; g++) {
+            ta.tab[g] = reinterpret_cast<const CellEntry*>(e.bh_peer[g] + e.bh_lay.off_celltab);
+            tt.blk[g] = reinterpret_cast<const float4*>(e.bh_peer[g] + e.bh_lay.off_nblk);
+            tt.cblk[g] = reinterpret_cast<const int4*>(e.bh_peer[g] + e.bh_lay.off_ncblk);
+            tt.acc[g] = reinterpret_cast<float2*>(e.bh_peer[g] + e.bh_lay.off_acc);
+        }
+    } else {
+        for (int r = 0; r < nparts; r++) {
+            ta.tab[r] = w.parts[r].celltab;
+            tt.blk[r] = w.parts[r].nblk;
+            tt.cblk[r] = w.parts[r].ncblk;
+        }
+        for (int g = 0; g < kMaxRanks; g++) tt.acc[g] = w.acc;
+    }
+    {
+        PhaseScope ps(e, 6);
+        ta.tcount = w.top.tcount; ta.tm3 = w.top.tm3; ta.tleaf = w.top.tleaf; ta.tchild = w.top.tchild;
+        ta.blk = w.top.blk; ta.cblk = w.top.cblk;
+        ta.top_off = static_cast<unsigned>(kMaxRanks) << kPartShift;
+        bh_top_build_kernel<<<1, 256, 0, s>>>(ta, w.status);
+        e.ctr.kernel_launches++;
+        tt.blk[kMaxRanks] = w.top.blk;
+        tt.cblk[kMaxRanks] = w.top.cblk;
+    }
+    {
+        PhaseScope ps(e, 0);
+        for (int r = 0; r < nparts; r++) {
+            if (real && r != e.rank) continue;
+            PartBufs& P = w.parts[real ? 0 : r];
+            if (P.n > 0) launch_traverse(e, tt, P.sx, P.sy, P.idx_sorted, nullptr, P.n, theta, w.status);
+        }
+    }
+    if (real) {
+        PhaseScope ps(e, 7);
+        // accelerations were scattered to their owners over NVLink: publish "my walk is done" and wait until
+        // every rank's walk is done (=> my acc buffer is complete and nobody reads my subtrees any more)
+        PeerU32 pf{};
+        for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags) + kMaxRanks;
+        bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
+        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags) + kMaxRanks, e.world, epoch);
+        e.ctr.kernel_launches += 2;
+        w.acc_src = reinterpret_cast<float2*>(e.bh_arena + e.bh_lay.off_acc);
+    } else {
+        w.acc_src = w.acc;
+    }
+    (void)nl;
+    w.last_partitioned = true;
+    NB_CUDA(cudaGetLastError());
 }
 
 // Deferred: the status block of a step is copied to pinned memory behind the step and looked at when the
@@ -822,7 +1340,10 @@ static void check_status(Engine& e, BhWork& w, bool sync_now) {
         fprintf(stderr, "nbody_b200: warning: quadtree node pool exhausted (%d nodes); deepest cells were merged\n", w.cap_nodes);
         w.warned = true;
     }
-    e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
+    if (w.last_partitioned)   // this rank's share; rank 0 (or the single process) also counts the shared top tree
+        e.ctr.bh_nodes_built += 4ull * static_cast<uint64_t>(h.n_deep) + (e.rank == 0 ? 1ull + 4ull * static_cast<uint64_t>(h.n_top) : 0ull);
+    else
+        e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
     e.ctr.bh_interactions += h.interactions;
     e.ctr.bh_nodes_visited += h.visited;
 }
@@ -837,7 +1358,7 @@ void bh_step(Engine& e, float theta, float dt) {
     {
         PhaseScope ps(e, 1);
         if (e.mode == NBX_MODE_EXACT) launch_integrate_exact(e, w.acc, dt, true);
-        else launch_integrate_fast(e, w.acc, 1, dt, true);
+        else launch_integrate_fast(e, w.acc_src, 1, dt, true);
     }
     e.step_count++;
     dist_signal_step_done(e);
@@ -850,7 +1371,7 @@ void bh_accelerations(Engine& e, float theta, float2* out) {
     BhWork& w = work(e);
     bh_forces(e, theta);
     if (e.mode == NBX_MODE_EXACT) launch_accel_from_force(e, w.acc, out);
-    else launch_accel_from_partial(e, w.acc, 1, out);
+    else launch_accel_from_partial(e, w.acc_src, 1, out);
     e.step_count++;
     dist_signal_step_done(e);
     check_status(e, w, true);
@@ -864,6 +1385,13 @@ void bh_shutdown(Engine& e) {
     fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
+    for (PartBufs& P : w.parts) {
+        fr(P.sel); fr(P.idx_sorted); fr(P.keys); fr(P.keys_sorted); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.w3); fr(P.p3);
+        fr(P.tile_sums); fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner);
+        if (!P.arena_owned) { fr(P.nblk); fr(P.ncblk); fr(P.celltab); }
+    }
+    fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.hist);
+    if (w.top.hist_host) cudaFreeHost(w.top.hist_host);
     delete &w;
     e.bh = nullptr;
 }

@@ -212,7 +212,9 @@ void dist_shutdown(Engine& e) {
     if (e.peers_mapped) {
         for (int g = 0; g < e.world; g++) {
             if (g != e.rank && e.peer[g].base) cudaIpcCloseMemHandle(e.peer[g].base);
+            if (g != e.rank && e.bh_peer[g]) cudaIpcCloseMemHandle(e.bh_peer[g]);
             e.peer[g].base = nullptr;
+            e.bh_peer[g] = nullptr;
         }
         e.peers_mapped = false;
     }
@@ -248,6 +250,11 @@ int dist_init(Engine& e, int rank, int world, int max_particles) {
     e.lay.set(L);
     NB_CUDA(cudaMalloc(&e.arena.base, e.lay.bytes));
     NB_CUDA(cudaMemset(e.arena.base, 0, e.lay.bytes));
+    if (world > 1) {
+        e.bh_lay.set(L);
+        NB_CUDA(cudaMalloc(&e.bh_arena, e.bh_lay.bytes));
+        NB_CUDA(cudaMemset(e.bh_arena, 0, e.bh_lay.bytes));
+    }
     e.rank = rank;
     e.world = world;
     e.max_particles = max_particles;
@@ -255,8 +262,9 @@ int dist_init(Engine& e, int rank, int world, int max_particles) {
     e.n = 0;
     e.step_count = 0;
     e.cur = 0;
-    for (int g = 0; g < kMaxRanks; g++) e.peer[g].base = nullptr;
+    for (int g = 0; g < kMaxRanks; g++) { e.peer[g].base = nullptr; e.bh_peer[g] = nullptr; }
     e.peer[rank] = e.arena;
+    e.bh_peer[rank] = e.bh_arena;
     e.peers_mapped = (world == 1);
     return 0;
 }
@@ -274,6 +282,15 @@ int dist_export(Engine& e, void* out) {
     }
     static_assert(sizeof(h) == 64, "IPC handle size");
     memcpy(out, &h, sizeof(h));
+    memset(static_cast<char*>(out) + 64, 0, 64);
+    if (e.bh_arena) {
+        err = cudaIpcGetMemHandle(&h, e.bh_arena);
+        if (err != cudaSuccess) {
+            set_error("cudaIpcGetMemHandle(bh arena): %s", cudaGetErrorString(err));
+            return -1;
+        }
+        memcpy(static_cast<char*>(out) + 64, &h, sizeof(h));
+    }
     return 0;
 }
 
@@ -285,7 +302,7 @@ int dist_import(Engine& e, const void* all, int world) {
     for (int g = 0; g < world; g++) {
         if (g == e.rank) continue;
         cudaIpcMemHandle_t h;
-        memcpy(&h, static_cast<const char*>(all) + 64 * g, 64);
+        memcpy(&h, static_cast<const char*>(all) + 128 * g, 64);
         void* p = nullptr;
         cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (err != cudaSuccess) {
@@ -294,6 +311,15 @@ int dist_import(Engine& e, const void* all, int world) {
             return -1;
         }
         e.peer[g].base = static_cast<char*>(p);
+        memcpy(&h, static_cast<const char*>(all) + 128 * g + 64, 64);
+        p = nullptr;
+        err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle(rank %d, bh arena): %s", g, cudaGetErrorString(err));
+            (void)cudaGetLastError();
+            return -1;
+        }
+        e.bh_peer[g] = static_cast<char*>(p);
     }
     e.peers_mapped = true;
     return 0;

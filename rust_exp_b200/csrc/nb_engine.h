@@ -42,6 +42,26 @@ struct ArenaLayout {
     }
 };
 
+// Second symmetric allocation, used by the domain-partitioned Barnes-Hut step (nb_bh.cu): this rank's
+// subtree blocks and cell table (walked in place by the peers over NVLink), the accelerations the peers
+// scatter to this rank's bodies, and two epoch-flag rows (trees ready / walks done).
+struct BhArenaLayout {
+    int cap_blocks = 0;
+    size_t off_nblk = 0, off_ncblk = 0, off_celltab = 0, off_acc = 0, off_flags = 0, bytes = 0;
+    void set(size_t shard_len) {
+        size_t cb = 3 * shard_len + 4096;
+        if (cb > (size_t(1) << 22) - 1) cb = (size_t(1) << 22) - 1;
+        cap_blocks = static_cast<int>(cb);
+        size_t o = 0;
+        off_nblk = o; o += cb * 64;
+        off_ncblk = o; o += cb * 16;
+        off_celltab = o; o += 1024 * 48;
+        off_acc = o; o += shard_len * 8;
+        off_flags = o; o += 2 * 64 * sizeof(uint32_t);
+        bytes = (o + 255) & ~size_t(255);
+    }
+};
+
 struct ArenaView {
     char* base = nullptr;
     float* x(const ArenaLayout& l, int b) const { return reinterpret_cast<float*>(base + l.off_x[b]); }
@@ -111,6 +131,10 @@ struct Engine {
     ArenaView arena;                 // own
     ArenaView peer[kMaxRanks];       // peer[rank] == arena
     bool peers_mapped = false;
+    BhArenaLayout bh_lay;
+    char* bh_arena = nullptr;        // own (sharded mode only)
+    char* bh_peer[kMaxRanks] = {};   // bh_peer[rank] == bh_arena
+    int bh_partition = 0;            // 0 auto, 1 force the replicated tree, >1 virtual parts on one GPU
     int cur = 0;                     // current position buffer
     uint32_t step_count = 0;         // steps completed (also the cross-rank flag value)
     // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies

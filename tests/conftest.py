@@ -38,6 +38,8 @@ def fresh(lib):
     lib.tune(0, 0, 0)
     lib.bh_count_interactions(False)
     lib.phase_timing(False)
+    lib.bh_partition(0)
     yield lib
     lib.set_mode(binding.MODE_FAST)
     lib.tune(0, 0, 0)
+    lib.bh_partition(0)

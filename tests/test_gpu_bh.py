@@ -162,6 +162,40 @@ def test_c5_size_4m_theta075_properties(fresh):
     assert np.array_equal(bits(a.astype(np.float32)), bits(b))
 
 
+# ------------------------------------------------------------------ domain-partitioned build -----------
+@pytest.mark.parametrize("n,theta,gen,parts", [(65536, 0.5, "disk", 2), (65536, 0.75, "plummer", 8), (100000, 0.5, "orbits", 4),
+                                               (262144, 0.5, "disk", 8)])
+def test_partitioned_tree_equals_single_tree(fresh, oracle, n, theta, gen, parts, monkeypatch):
+    """The multi-GPU code path (cell-aligned Morton partition, per-part subtree forests, shared top tree,
+    part-tagged block indices) run with `parts` virtual ranks on one GPU: same quadtree as the reference
+    (node count), same interaction lists (counts), same forces as the single-tree walk to rounding."""
+    monkeypatch.setenv("NB_BH_PARTS_MIN_N", "0")
+    s = ic.stable_orbits(n, 0.5, 30.0, seed=4) if gen == "orbits" else \
+        (ic.random_disk(n, seed=4) if gen == "disk" else ic.plummer_2d(n, seed=4))
+    fresh.bh_count_interactions(True)
+    fresh.set_particles(s)
+    fresh.bh_partition(1)
+    fresh.reset_counters()
+    a1 = fresh.bh_accelerations(theta).astype(np.float64)
+    c1 = fresh.counters()
+    fresh.bh_partition(parts)
+    fresh.reset_counters()
+    a2 = fresh.bh_accelerations(theta).astype(np.float64)
+    c2 = fresh.counters()
+    oracle.set_particles(s)
+    oracle.bh_build()
+    assert c1["bh_nodes_built"] == oracle.bh_node_count()
+    assert c2["bh_nodes_built"] == oracle.bh_node_count()
+    assert abs(c2["bh_interactions"] - c1["bh_interactions"]) <= 1e-5 * c1["bh_interactions"]
+    assert abs(c2["bh_nodes_visited"] - c1["bh_nodes_visited"]) <= 1e-5 * c1["bh_nodes_visited"]
+    err = np.abs(a2 - a1).max(1) / np.abs(a1).max()
+    assert np.quantile(err, 0.999) <= 1e-6 and err.max() <= 2e-3
+    # and a few steps through the partitioned path stay within tolerance of the oracle
+    g = run_gpu(fresh, s, theta, 0.01, 3)
+    r = run_ora(oracle, s, theta, 0.01, 3, nthreads=os.cpu_count() or 1)
+    assert np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max() / np.abs(r[:, :2]).max() <= 1e-4
+
+
 def test_theta_zero_goes_brute_force(fresh, oracle):
     s = ic.random_disk(1500, seed=9)
     fresh.set_mode(binding.MODE_EXACT)
