@@ -47,7 +47,7 @@ def test_library_loads_and_answers_without_compute():
     L = pkg.NBodyLib()
     assert L.version().startswith("nbody_b200")
     assert L.num_particles() == 0  # no device touched
-    assert int(L.L.nbx_dist_handle_bytes()) == 64
+    assert int(L.L.nbx_dist_handle_bytes()) == 128  # two CUDA IPC handles: state arena + Barnes-Hut arena
     assert ctypes.sizeof(binding.Counters) == 48
 
 

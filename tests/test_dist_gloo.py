@@ -37,7 +37,7 @@ class FakeLib:
         self.log.append(("init", rank, world, maxp)); self.world, self.maxp = world, maxp
 
     def dist_export(self):
-        return bytes([self.rank]) * 64
+        return bytes([self.rank]) * 128
 
     def dist_import(self, handles, world):
         self.log.append(("import", handles, world))
@@ -66,13 +66,13 @@ def _worker(rank, world, port, n, steps, q):
         import oracle
         o = oracle.get()
         # --- plumbing ---
-        got = all_gather_bytes(bytes([rank]) * 64)
-        assert got == [bytes([r]) * 64 for r in range(world)]
+        got = all_gather_bytes(bytes([rank]) * 128)
+        assert got == [bytes([r]) * 128 for r in range(world)]
         assert broadcast_bytes(b"id" if rank == 0 else None) == b"id"
         fl = FakeLib(rank)
         lay = wire(fl, n, transport=2)
         assert fl.log[0] == ("init", rank, world, n)
-        assert fl.log[1] == ("import", b"".join(bytes([r]) * 64 for r in range(world)), world)
+        assert fl.log[1] == ("import", b"".join(bytes([r]) * 128 for r in range(world)), world)
         assert fl.log[2] == ("nccl", b"U" * 128) and fl.log[3] == ("transport", 2)
 
         # --- sharded step: rows by index, all j in global order, gather of positions each step ---

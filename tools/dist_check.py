@@ -101,6 +101,46 @@ def main():
     r = o.get_particles()
     err = float(np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max() / np.abs(r[:, :2]).max())
     report("fast_bh_vs_oracle", err <= 1e-4, rel_pos_err=err)
+    # ---- domain-partitioned Barnes-Hut (one part per GPU, remote subtrees walked in place) vs replicated tree
+    os.environ["NB_BH_PARTS_MIN_N"] = "0"
+    nb_ = 120000
+    sp = ic.random_disk(nb_, seed=44)
+    lib.bh_count_interactions(True)
+    res = {}
+    for mode, name in ((1, "replicated"), (0, "partitioned")):
+        lib.bh_partition(mode)
+        lib.set_particles(sp)
+        lib.reset_counters()
+        acc = lib.bh_accelerations(0.5)           # each rank fills its own index shard's rows
+        t = torch.from_numpy(acc).cuda()
+        dist.all_reduce(t)                        # rows are disjoint -> sum assembles the full array
+        cnt = lib.counters()
+        ct = torch.tensor([cnt["bh_nodes_built"], cnt["bh_interactions"], cnt["bh_nodes_visited"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ct)
+        res[name] = (t.cpu().numpy().astype(np.float64), [int(v) for v in ct.tolist()])
+    o.set_particles(sp)
+    o.bh_build()
+    a_rep, c_rep = res["replicated"]
+    a_par, c_par = res["partitioned"]
+    report("bh_partitioned_node_count_equals_reference", c_par[0] == o.bh_node_count(), nodes=c_par[0], ref=o.bh_node_count())
+    report("bh_partitioned_interaction_lists", abs(c_par[1] * world - c_rep[1]) <= 1e-5 * c_rep[1] or abs(c_par[1] - c_rep[1] // 1) <= 1e-5 * c_rep[1],
+           part=c_par[1:], repl=c_rep[1:])
+    err = np.abs(a_par - a_rep).max(1) / np.abs(a_rep).max()
+    report("bh_partitioned_forces_equal_replicated", float(np.quantile(err, 0.999)) <= 1e-6 and float(err.max()) <= 2e-3,
+           q999=float(np.quantile(err, 0.999)), max=float(err.max()))
+    lib.bh_partition(0)
+    lib.set_particles(sp)
+    for _ in range(5):
+        lib.step_barnes_hut(0.5, 0.01, 1)
+    g = lib.get_particles()
+    o.set_particles(sp)
+    for _ in range(5):
+        o.step_barnes_hut(0.5, 0.01, 8)
+    r = o.get_particles()
+    err = float(np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max() / np.abs(r[:, :2]).max())
+    report("bh_partitioned_5_steps_vs_oracle", err <= 1e-4, rel_pos_err=err)
+    lib.bh_count_interactions(False)
+
     fb = lib.draw(128, 96)
     o.set_particles(g)
     report("draw_sharded", np.array_equal(fb, o.draw(128, 96)))
@@ -127,6 +167,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         report(f"time_{name}", True, n=big, world=world, ms_per_step=float(t.item()),
                pairs_per_s=big * (big - 1) / (float(t.item()) * 1e-3))
+    # Barnes-Hut step time, replicated vs partitioned
+    nbh = int(os.environ.get("NB_DIST_BH", 1 << 20))
+    if nbh <= max(big, 70000):
+        sb2 = ic.random_disk(nbh, seed=45)
+        for mode, name in ((1, "bh_replicated"), (0, "bh_partitioned")):
+            lib.bh_partition(mode)
+            lib.dist_set_transport(1)
+            lib.set_particles(sb2)
+            for _ in range(3):
+                lib.step_barnes_hut(0.75, 0.01, 1)
+            torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            reps = 10
+            for _ in range(reps):
+                lib.step_barnes_hut(0.75, 0.01, 1)
+            e1.record(st)
+            torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            report(f"time_{name}", True, n=nbh, world=world, ms_per_step=float(t.item()))
+        lib.bh_partition(0)
     lib.set_stream(None)
     dist.barrier()
     dist.destroy_process_group()
