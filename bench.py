@@ -35,9 +35,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_PAIR = 12  # <2,REF>: 2 sub + 2 FMA + rcp + mul + 2 FMA
+FLOP_PER_PAIR_3D_NEWTON = 20  # <3,NEWTON>: 3 sub + 3 FMA + rsqrt + 2 mul (cube) + mul + 3 FMA (GPU Gems 3 ch.31 convention)
 WORKLOADS = {
     "c2": dict(n=65536, kind="allpairs", ic="plummer", seed=2, desc="65,536-body Plummer (2-D), all-pairs"),
     "c3": dict(n=1 << 20, kind="allpairs", ic="plummer", seed=3, desc="1,048,576-body Plummer (2-D), all-pairs"),
+    "c2n": dict(n=65536, kind="allpairs3", ic="plummer3", seed=2, desc="65,536-body Plummer sphere, 3-D Newtonian (rsqrt) all-pairs [nbx3 extension]"),
+    "c3n": dict(n=1 << 20, kind="allpairs3", ic="plummer3", seed=3, desc="1,048,576-body Plummer sphere, 3-D Newtonian (rsqrt) all-pairs [nbx3 extension]"),
     "c4": dict(n=262144, kind="bh", theta=0.5, ic="disk", seed=4, desc="262,144-body uniform disk, Barnes-Hut theta=0.5"),
     "c5": dict(n=1 << 22, kind="bh", theta=0.75, ic="disk", seed=5, desc="4,194,304-body uniform disk, Barnes-Hut theta=0.75"),
 }
@@ -50,6 +53,8 @@ TRAFFIC_NCU = {("c3", 1): 28.21e6 + 130.74e6}
 def make_ic(w):
     from rust_exp_b200 import ic
 
+    if w["ic"] == "plummer3":
+        return ic.plummer_3d(w["n"], seed=w["seed"])
     if w["ic"] == "plummer":
         return ic.plummer_2d(w["n"], seed=w["seed"])
     return ic.random_disk(w["n"], seed=w["seed"])
@@ -267,14 +272,24 @@ def main():
         nbdist.wire(lib, n, transport)
 
     # pinned host state (the e2e leg copies from / to it every step)
-    host = torch.empty((n, 5), dtype=torch.float32, pin_memory=True)
+    is3 = w["kind"] == "allpairs3"
+    if is3 and world > 1:
+        raise SystemExit("the nbx3 extension workloads are single-GPU")
+    width = 7 if is3 else 5
+    host = torch.empty((n, width), dtype=torch.float32, pin_memory=True)
     host.numpy()[:] = make_ic(w)
-    host_out = torch.empty((n, 5), dtype=torch.float32, pin_memory=True)
-    lib.set_particles(host.numpy())
+    host_out = torch.empty((n, width), dtype=torch.float32, pin_memory=True)
+    if is3:
+        lib.configure3(binding.LAW3_NEWTON, 1e-4)
+        lib.set_particles3(host.numpy())
+    else:
+        lib.set_particles(host.numpy())
 
     def step():
         if w["kind"] == "allpairs":
             lib.step_brute_force(DT)
+        elif is3:
+            lib.step3(DT)
         else:
             lib.step_barnes_hut(w["theta"], DT, 1)
 
@@ -337,6 +352,11 @@ def main():
     barrier()
     te0 = time.perf_counter()
     for _ in range(e2e_steps):
+        if is3:
+            lib.set_particles3(host.numpy())
+            step()
+            lib.L.nbx3_get_particles(host_out.numpy().ctypes.data, n)
+            continue
         lib.set_particles(host.numpy())        # H2D (each rank uploads its shard of the pinned array)
         step()
         lib.get_particles(host_out.numpy())    # D2H of the full state (synchronises)
@@ -346,33 +366,34 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item()) / e2e_steps
     b, c = lib.dist_local_range() if world > 1 else (0, n)
-    h2d = torch.tensor([20 * c], dtype=torch.int64, device="cuda")
+    h2d = torch.tensor([4 * width * c], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(h2d)
-    d2h = 20 * n * world
+    d2h = 4 * width * n * world
 
     pk = peaks()
     sm_max = pk.get("sm_max_mhz", 1965.0)
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp32_peak = 2 * 128 * sms * sm_max * 1e6 / 1e12  # TFLOP/s, SURVEY.md H9
 
-    if w["kind"] == "allpairs":
+    if w["kind"] in ("allpairs", "allpairs3"):
+        fpp = FLOP_PER_PAIR_3D_NEWTON if is3 else FLOP_PER_PAIR
         pairs_per_step = n * (n - 1)
         value = pairs_per_step * args.steps / (ms * 1e-3)
         e2e_value = pairs_per_step / e2e_s
         metric, unit = "pair-interactions/s", "pair-interactions/s"
-        force_ms = phases["force"]
+        force_ms = phases["force"] if not is3 else ms_per_step   # nbx3 has no phase events: 2 kernels, integrate ~0.01 ms
         # dominant kernel = allpairs_fast_kernel: each rank's launch evaluates n_local*(n-1) pairs
         per_launch_pairs = (n // world) * (n - 1)
-        achieved = per_launch_pairs * FLOP_PER_PAIR / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
-        roofline = {"bound": "fp32", "kernel": "allpairs_fast_kernel", "achieved": achieved, "peak": fp32_peak,
+        achieved = per_launch_pairs * fpp / (force_ms * 1e-3) / 1e12 if force_ms > 0 else None
+        roofline = {"bound": "fp32", "kernel": "allpairs3_kernel<NEWTON>" if is3 else "allpairs_fast_kernel", "achieved": achieved, "peak": fp32_peak,
                     "unit": "TFLOP/s", "frac": achieved / fp32_peak if achieved else None,
                     "traffic": TRAFFIC_NCU.get((args.workload, world)),
-                    "flop_per_pair": FLOP_PER_PAIR, "kernel_ms": force_ms, "kernel_share_of_step": force_ms / ms_per_step,
+                    "flop_per_pair": fpp, "kernel_ms": force_ms, "kernel_share_of_step": force_ms / ms_per_step,
                     "peak_source": f"computed 2*128*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; sm_max_mhz is from it); "
                                    "the kernel is co-limited by the MUFU pipe at 75% of this (DESIGN.md section 4)",
                     "mufu_bound_frac": (achieved / (0.75 * fp32_peak)) if achieved else None}
-        extra = {"fp32_tflops": value * FLOP_PER_PAIR / 1e12, "fp32_frac_of_peak_all_gpus": value * FLOP_PER_PAIR / 1e12 / (fp32_peak * world)}
+        extra = {"fp32_tflops": value * fpp / 1e12, "fp32_frac_of_peak_all_gpus": value * fpp / 1e12 / (fp32_peak * world)}
     else:
         value = n * args.steps / (ms * 1e-3)
         e2e_value = n / e2e_s
@@ -419,7 +440,12 @@ def main():
     line.update(extra)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         st = host.numpy().copy()
-        line["cpu_baseline"] = cpu_baseline_allpairs(st) if w["kind"] == "allpairs" else cpu_baseline_bh(st, w["theta"])
+        if w["kind"] == "allpairs":
+            line["cpu_baseline"] = cpu_baseline_allpairs(st)
+        elif w["kind"] == "bh":
+            line["cpu_baseline"] = cpu_baseline_bh(st, w["theta"])
+        else:
+            line["cpu_baseline"] = None   # the reference has no 3-D path
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

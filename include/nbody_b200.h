@@ -133,6 +133,21 @@ int32_t nbx_accelerations(float *axy_out, int32_t n);
 /* Same through the Barnes-Hut tree (build + traversal with opening angle theta, no state update). */
 int32_t nbx_bh_accelerations(float theta, float *axy_out, int32_t n);
 
+/* ---- 3-D extension (NOT part of the drop-in surface) ------------------------------------
+ * A separate particle set of 7-float records {px,py,pz,vx,vy,vz,m} and an all-pairs step with a selectable
+ * pair law.  LAW_NEWTON: a_i = sum m_j d/(|d|^2+eps2)^(3/2) (rsqrt-based, 20 flop/pair -- the kernel the
+ * project brief describes).  LAW_REF: the reference's un-normalised law m_j d/(|d|^2+eps2) lifted to 3-D; with
+ * z == 0 it reproduces the 2-D FAST kernel bit for bit.  Single GPU.  Integrator as in the reference
+ * (rs-src/nbody.rs:153-160).  Default: LAW_NEWTON, eps2 = 1e-4. */
+#define NBX3_LAW_NEWTON 0
+#define NBX3_LAW_REF 1
+int32_t nbx3_num_particles(void);
+int32_t nbx3_set_particles(const float *aos7, int32_t n);
+int32_t nbx3_get_particles(float *aos7_out, int32_t n);
+int32_t nbx3_configure(int32_t law, float eps2);
+int32_t nbx3_step_all_pairs(float dt);
+int32_t nbx3_accelerations(float *axyz_out, int32_t n);
+
 /* ---- multi-GPU (one process per GPU; particles shard by index) -------------
  * Wiring is done by the host framework's process group (torch.distributed in this repo):
  *   1. every rank: nbx_dist_init(rank, world, max_particles) -> allocates the symmetric arena

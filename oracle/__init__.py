@@ -51,6 +51,8 @@ class Oracle:
         L.ora_bh_forces_rows.argtypes = [f, i32, i32, vp]
         L.ora_bh_count.argtypes = [f, vp, vp]
         L.ora_accel_f64_rows.argtypes = [vp, i32, vp]
+        L.ora3_accel_f64.argtypes = [vp, i32, i32, C.c_double, vp, i32, vp]
+        L.ora3_step_f64.argtypes = [vp, i32, i32, C.c_double, C.c_double]
         L.ora_draw.argtypes = [i32, i32, vp]
         L.ora_rgb_to_abgr32.argtypes = [C.c_uint8, C.c_uint8, C.c_uint8, f]
         L.ora_rgb_to_abgr32.restype = C.c_uint32
@@ -134,6 +136,23 @@ class Oracle:
         out = np.empty((r.shape[0], 2), dtype=np.float64)
         self.L.ora_accel_f64_rows(r.ctypes.data, r.shape[0], out.ctypes.data)
         return out
+
+    # -- 3-D extension checker (f64) ---------------------------------------------------------
+    def accel3_f64(self, state7: np.ndarray, law: int, eps2: float, rows: np.ndarray | None = None) -> np.ndarray:
+        s = np.ascontiguousarray(state7, dtype=np.float64).reshape(-1, 7)
+        if rows is None:
+            out = np.empty((s.shape[0], 3), dtype=np.float64)
+            self.L.ora3_accel_f64(s.ctypes.data, s.shape[0], law, eps2, None, s.shape[0], out.ctypes.data)
+        else:
+            r = np.ascontiguousarray(rows, dtype=np.int32)
+            out = np.empty((r.shape[0], 3), dtype=np.float64)
+            self.L.ora3_accel_f64(s.ctypes.data, s.shape[0], law, eps2, r.ctypes.data, r.shape[0], out.ctypes.data)
+        return out
+
+    def step3_f64(self, state7: np.ndarray, law: int, eps2: float, dt: float) -> np.ndarray:
+        s = np.array(state7, dtype=np.float64, copy=True).reshape(-1, 7)
+        self.L.ora3_step_f64(s.ctypes.data, s.shape[0], law, eps2, dt)
+        return s
 
     # -- draw -------------------------------------------------------------------------------
     def draw(self, w: int, h: int) -> np.ndarray:

@@ -529,6 +529,42 @@ void ora_accel_f64_rows(const int32_t *rows, int32_t nrows, double *axy_out)
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * 3-D extension checker (not in the reference, which is 2-D): f64 evaluation of the two pair laws the
+ * nbx3_* kernels implement.  law 0: m_j d/(|d|^2+eps2)^(3/2) (Newtonian); law 1: m_j d/(|d|^2+eps2).
+ * state7 = {px,py,pz,vx,vy,vz,m} per body.
+ * ------------------------------------------------------------------------------------------- */
+void ora3_accel_f64(const double *state7, int32_t n, int32_t law, double eps2, const int32_t *rows, int32_t nrows,
+                    double *axyz_out)
+{
+    for (int32_t r = 0; r < nrows; r++) {
+        const int32_t i = rows ? rows[r] : r;
+        const double xi = state7[7 * i], yi = state7[7 * i + 1], zi = state7[7 * i + 2];
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        for (int32_t j = 0; j < n; j++) {
+            if (j == i) continue;
+            const double dx = state7[7 * j] - xi, dy = state7[7 * j + 1] - yi, dz = state7[7 * j + 2] - zi;
+            const double d2 = dx * dx + dy * dy + dz * dz + eps2;
+            const double s = state7[7 * j + 6] / (law == 0 ? d2 * sqrt(d2) : d2);
+            ax += s * dx; ay += s * dy; az += s * dz;
+        }
+        axyz_out[3 * r] = ax; axyz_out[3 * r + 1] = ay; axyz_out[3 * r + 2] = az;
+    }
+}
+/* semi-implicit Euler (rs-src/nbody.rs:153-160) in f64 */
+void ora3_step_f64(double *state7, int32_t n, int32_t law, double eps2, double dt)
+{
+    double *a = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+    ora3_accel_f64(state7, n, law, eps2, NULL, n, a);
+    for (int32_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) {
+            state7[7 * i + 3 + k] += dt * a[3 * i + k];
+            state7[7 * i + k] += dt * state7[7 * i + 3 + k];
+        }
+    }
+    free(a);
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Draw.  rs-src/nbody.rs:482-617.
  * ------------------------------------------------------------------------------------------- */
 

@@ -45,6 +45,12 @@ SYMBOLS = {
     "nbx_get_phase_ms": (i32, [vp]),
     "nbx_accelerations": (i32, [vp, i32]),
     "nbx_bh_accelerations": (i32, [f32, vp, i32]),
+    "nbx3_num_particles": (i32, []),
+    "nbx3_set_particles": (i32, [vp, i32]),
+    "nbx3_get_particles": (i32, [vp, i32]),
+    "nbx3_configure": (i32, [i32, f32]),
+    "nbx3_step_all_pairs": (i32, [f32]),
+    "nbx3_accelerations": (i32, [vp, i32]),
     "nbx_dist_init": (i32, [i32, i32, i32]),
     "nbx_dist_handle_bytes": (i32, []),
     "nbx_dist_export": (i32, [vp]),
@@ -57,6 +63,7 @@ SYMBOLS = {
 
 MODE_FAST, MODE_EXACT = 0, 1
 TRANSPORT_P2P_DIRECT, TRANSPORT_P2P_GATHER, TRANSPORT_NCCL = 0, 1, 2
+LAW3_NEWTON, LAW3_REF = 0, 1
 PHASES = ("force", "integrate", "aabb", "keys", "sort", "build", "com", "xrank")
 
 
@@ -194,6 +201,29 @@ class NBodyLib:
         n = self.num_particles() if n is None else n
         out = np.zeros((n, 2), dtype=np.float32)
         self._chk(self.L.nbx_bh_accelerations(theta, out.ctypes.data, n), "nbx_bh_accelerations")
+        return out
+
+    # ---- 3-D extension ----------------------------------------------------------------------------
+    def set_particles3(self, aos7: np.ndarray) -> None:
+        a = np.ascontiguousarray(aos7, dtype=np.float32).reshape(-1, 7)
+        self._chk(self.L.nbx3_set_particles(a.ctypes.data, a.shape[0]), "nbx3_set_particles")
+
+    def get_particles3(self) -> np.ndarray:
+        n = int(self.L.nbx3_num_particles())
+        out = np.empty((n, 7), dtype=np.float32)
+        self._chk(self.L.nbx3_get_particles(out.ctypes.data, n), "nbx3_get_particles")
+        return out
+
+    def configure3(self, law: int, eps2: float = 1e-4) -> None:
+        self._chk(self.L.nbx3_configure(law, eps2), "nbx3_configure")
+
+    def step3(self, dt: float) -> None:
+        self._chk(self.L.nbx3_step_all_pairs(dt), "nbx3_step_all_pairs")
+
+    def accelerations3(self) -> np.ndarray:
+        n = int(self.L.nbx3_num_particles())
+        out = np.zeros((n, 3), dtype=np.float32)
+        self._chk(self.L.nbx3_accelerations(out.ctypes.data, n), "nbx3_accelerations")
         return out
 
     # ---- multi-GPU -------------------------------------------------------------------------------

@@ -117,6 +117,7 @@ void nbx_shutdown(void) {
     cudaStreamSynchronize(e.stream);
     dist_shutdown(e);
     bh_shutdown(e);
+    x3_shutdown(e);
     if (e.arena.base) cudaFree(e.arena.base);
     if (e.bh_arena) cudaFree(e.bh_arena);
     e.bh_arena = nullptr;
@@ -275,6 +276,54 @@ int32_t nbx_bh_accelerations(float theta, float* axy_out, int32_t n) {
         NB_CUDA(cudaMemcpyAsync(axy_out + 2 * static_cast<size_t>(b), e.force, sizeof(float2) * c, cudaMemcpyDeviceToHost,
                                 e.stream));
     NB_CUDA(cudaStreamSynchronize(e.stream));
+    return 0;
+}
+
+int32_t nbx3_num_particles(void) {
+    NB_LOCK();
+    return engine().inited ? x3_num(engine()) : 0;
+}
+int32_t nbx3_set_particles(const float* aos7, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    x3_set(e, aos7, n);
+    return 0;
+}
+int32_t nbx3_get_particles(float* aos7_out, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    x3_get(e, aos7_out, n);
+    return 0;
+}
+int32_t nbx3_configure(int32_t law, float eps2) {
+    NB_LOCK();
+    if ((law != NBX3_LAW_NEWTON && law != NBX3_LAW_REF) || !(eps2 > 0.0f)) {
+        set_error("nbx3_configure: law must be NBX3_LAW_NEWTON or NBX3_LAW_REF and eps2 > 0");
+        return -1;
+    }
+    Engine& e = engine();
+    ensure_init(e);
+    x3_config(e, law, eps2);
+    return 0;
+}
+int32_t nbx3_step_all_pairs(float dt) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    x3_step(e, dt, 1, nullptr);
+    return 0;
+}
+int32_t nbx3_accelerations(float* axyz_out, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    if (n < x3_num(e)) {
+        set_error("nbx3_accelerations: output holds %d bodies, the set has %d", n, x3_num(e));
+        return -1;
+    }
+    x3_step(e, 0.0f, 0, axyz_out);
     return 0;
 }
 

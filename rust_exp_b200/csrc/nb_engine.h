@@ -169,6 +169,8 @@ struct Engine {
 
     // Barnes-Hut workspace, opaque (nb_bh.cu)
     void* bh = nullptr;
+    // 3-D extension state, opaque (nb_3d.cu)
+    void* ext3 = nullptr;
 };
 
 Engine& engine();
@@ -224,6 +226,14 @@ void bh_step(Engine& e, float theta, float dt);
 void bh_accelerations(Engine& e, float theta, float2* out);
 void bh_shutdown(Engine& e);
 void bh_poll(Engine& e);   // fold the last Barnes-Hut step's status/counters in (synchronises)
+
+// nb_3d.cu
+void x3_set(Engine& e, const float* aos7, int n);
+void x3_get(Engine& e, float* aos7, int n);
+int x3_num(Engine& e);
+void x3_config(Engine& e, int law, float eps2);
+void x3_step(Engine& e, float dt, int update, float* acc_host);
+void x3_shutdown(Engine& e);
 
 // nb_draw.cu
 void draw_to_host(Engine& e, int w, int h, uint32_t* fb);

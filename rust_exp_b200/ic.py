@@ -62,3 +62,22 @@ def plummer_2d(n: int, seed: int = 2, a_scale: float = 5.0, total_mass_per_body:
     out[:, 3] = rng.normal(0, 1, n) * sigma
     out[:, 4] = m
     return out
+
+
+def plummer_3d(n: int, seed: int = 2, a_scale: float = 5.0, mass_per_body: float = 1e-2) -> np.ndarray:
+    """Plummer sphere for the 3-D extension: (N,7) float32 {px,py,pz,vx,vy,vz,m}, truncated at 10a."""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 7), dtype=np.float32)
+    xmax = (10.0**3) / (101.0**1.5)
+    u = rng.random(n) * xmax
+    r = a_scale / np.sqrt(u ** (-2.0 / 3.0) - 1.0)
+    cz = rng.uniform(-1, 1, n)
+    ph = rng.uniform(0, 2 * np.pi, n)
+    s = np.sqrt(1 - cz * cz)
+    out[:, 0] = r * s * np.cos(ph)
+    out[:, 1] = r * s * np.sin(ph)
+    out[:, 2] = r * cz
+    sigma = np.sqrt(n * mass_per_body / (6.0 * a_scale)) * (1 + (r / a_scale) ** 2) ** (-0.25)
+    out[:, 3:6] = rng.normal(0, 1, (n, 3)) * sigma[:, None]
+    out[:, 6] = mass_per_body
+    return out

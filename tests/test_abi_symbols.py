@@ -17,7 +17,7 @@ def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"typedef struct.*?\}\s*\w+;", "", src, flags=re.S)
-    names = re.findall(r"\b(nbx?_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b(nbx?3?_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
