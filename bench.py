@@ -319,25 +319,38 @@ def main():
         barrier()
 
     lib.reset_counters()
-    lib.phase_timing(True)
+    # All-pairs: the library's per-phase events ride along in the timed region (2 kernels per step, the extra
+    # event pairs are noise).  Barnes-Hut: a step is ~15 short kernels, so the timed region runs WITHOUT them
+    # and the per-phase times come from a second, instrumented pass of the same steps afterwards.
+    phases_in_timed_region = w["kind"] != "bh"
+    lib.phase_timing(phases_in_timed_region)
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # K steps, each bracketed by its own CUDA-event pair on the library's stream; the L2 flush (a 256 MiB
+    # memset, ~70 us) runs BETWEEN the timed iterations, outside the event pairs.  ms = sum of the K step times.
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
+    for a, b in evs:
+        a.record(stream)
         step()
-        flush.zero_()  # L2 flush between timed iterations (inside the timed region; ~0.1 ms each)
-    e1.record(stream)
+        b.record(stream)
+        flush.zero_()
     barrier()
     t1 = time.perf_counter()
-    ms = e0.elapsed_time(e1)
+    ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop(t0, t1)
-    phases = lib.phase_ms()
-    lib.phase_timing(False)
     ctr = lib.counters()
+    if phases_in_timed_region:
+        phases = lib.phase_ms()
+    else:
+        lib.phase_timing(True)
+        for _ in range(min(args.steps, 20)):
+            step()
+            flush.zero_()
+        phases = lib.phase_ms()
+    lib.phase_timing(False)
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -392,7 +405,10 @@ def main():
                     "flop_per_pair": fpp, "kernel_ms": force_ms, "kernel_share_of_step": force_ms / ms_per_step,
                     "peak_source": f"computed 2*128*{sms} SMs*{sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 figure; sm_max_mhz is from it); "
                                    "the kernel is co-limited by the MUFU pipe at 75% of this (DESIGN.md section 4)",
-                    "mufu_bound_frac": (achieved / (0.75 * fp32_peak)) if achieved else None}
+                    "mufu_bound_frac": (achieved / (0.75 * fp32_peak)) if achieved else None,
+                    # measured on this pool's B200 with rust_exp_b200/nb_microbench (profiles/r01_microbench_pipes.jsonl):
+                    # packed-FP32 FFMA2 sustains 71.3 TFLOP/s (95.7 % of nominal), MUFU.RCP 4.62e12/s
+                    "peak_measured_ffma2": 71.3, "frac_of_measured_ffma2": (achieved / 71.3) if achieved else None}
         extra = {"fp32_tflops": value * fpp / 1e12, "fp32_frac_of_peak_all_gpus": value * fpp / 1e12 / (fp32_peak * world)}
     else:
         value = n * args.steps / (ms * 1e-3)
@@ -427,7 +443,7 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {w['desc']}", "n_bodies": n, "dt": DT, "mode": "fast",
                    "parallelism": f"index-sharded x{world}" + (f", transport={args.transport}" if world > 1 else ""),
-                   "l2": "flushed between timed steps (256 MiB memset inside the timed region); the 12 MiB position set is re-read from L2 by design",
+                   "l2": "flushed between timed steps (256 MiB memset between the per-step CUDA-event pairs); within a step the position set is re-read from L2 by design",
                    "ic": w["ic"], "seed": w["seed"]},
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
