@@ -129,6 +129,17 @@ struct BhWork {
     bool warned = false;
     bool status_pending = false;
     cudaEvent_t status_ev = nullptr;
+    // CUDA graph of the single-GPU FAST step (one per position-buffer parity): ~20 short launches replayed as one
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        int n = -1, cur = -1;
+        float theta = 0.f, dt = 0.f;
+        cudaStream_t stream = nullptr;
+        uint64_t launches = 0;
+        const char* arena = nullptr;
+    } graph[2];
+    int graph_misses = 0;
+    bool capturing = false;
     // domain-partitioned mode
     std::vector<PartBufs> parts;
     TopBufs top;
@@ -922,8 +933,10 @@ static void bh_forces(Engine& e, float theta) {
     }
     NB_CUDA(cudaGetLastError());
     NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
-    NB_CUDA(cudaEventRecord(w.status_ev, s));
-    w.status_pending = true;
+    if (!w.capturing) {
+        NB_CUDA(cudaEventRecord(w.status_ev, s));
+        w.status_pending = true;
+    }
 }
 
 // =================================================================================================
@@ -1351,14 +1364,63 @@ void bh_poll(Engine& e) {
     if (e.bh) check_status(e, work(e), true);
 }
 
+static void bh_step_body(Engine& e, BhWork& w, float theta, float dt) {
+    bh_forces(e, theta);
+    PhaseScope ps(e, 1);
+    if (e.mode == NBX_MODE_EXACT) launch_integrate_exact(e, w.acc, dt, true);
+    else launch_integrate_fast(e, w.acc_src, 1, dt, true);
+}
+
+// The single-GPU FAST step is a fixed sequence of ~20 short kernels whose launch configuration depends only on
+// n: capture it once per position-buffer parity and replay it (NB_BH_GRAPH=0 disables).
+static bool bh_graph_eligible(const Engine& e) {
+    if (e.mode != NBX_MODE_FAST || e.phase_timing || e.bh_count || (e.dist && e.world > 1)) return false;
+    if (bh_partition_count(e) > 1) return false;
+    if (const char* s = getenv("NB_BH_GRAPH")) return atoi(s) != 0;
+    return true;
+}
+
 void bh_step(Engine& e, float theta, float dt) {
     if (e.n == 0) return;
     BhWork& w = work(e);
-    bh_forces(e, theta);
-    {
-        PhaseScope ps(e, 1);
-        if (e.mode == NBX_MODE_EXACT) launch_integrate_exact(e, w.acc, dt, true);
-        else launch_integrate_fast(e, w.acc_src, 1, dt, true);
+    if (bh_graph_eligible(e) && w.graph_misses < 16) {
+        ensure_status(w);
+        check_status(e, w, false);
+        ensure_work(e, w, e.n);
+        if (local_count(e) > w.cap_acc) {   // same sizing rule as bh_forces: allocate outside the capture
+            if (w.acc) NB_CUDA(cudaFree(w.acc));
+            NB_CUDA(cudaMalloc(&w.acc, sizeof(float2) * static_cast<size_t>(e.lay.L)));
+            w.cap_acc = static_cast<int>(e.lay.L);
+        }
+        BhWork::GraphSlot& g = w.graph[e.cur];
+        const bool hit = g.exec && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
+                         g.arena == e.arena.base;
+        if (!hit) {
+            if (g.exec) { NB_CUDA(cudaGraphExecDestroy(g.exec)); g.exec = nullptr; w.graph_misses++; }
+            const int cur0 = e.cur;
+            const uint64_t l0 = e.ctr.kernel_launches;
+            cudaGraph_t graph = nullptr;
+            w.capturing = true;
+            NB_CUDA(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
+            bh_step_body(e, w, theta, dt);
+            NB_CUDA(cudaStreamEndCapture(e.stream, &graph));
+            w.capturing = false;
+            NB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+            NB_CUDA(cudaGraphDestroy(graph));
+            g.n = e.n; g.cur = cur0; g.theta = theta; g.dt = dt; g.stream = e.stream; g.arena = e.arena.base;
+            g.launches = e.ctr.kernel_launches - l0;
+            // the capture already advanced the host-side state exactly like a replay does below
+        } else {
+            e.ctr.kernel_launches += g.launches;
+            e.cur ^= 1;
+            w.acc_src = w.acc;
+            w.last_partitioned = false;
+        }
+        NB_CUDA(cudaGraphLaunch(g.exec, e.stream));
+        NB_CUDA(cudaEventRecord(w.status_ev, e.stream));
+        w.status_pending = true;
+    } else {
+        bh_step_body(e, w, theta, dt);
     }
     e.step_count++;
     dist_signal_step_done(e);
@@ -1385,6 +1447,7 @@ void bh_shutdown(Engine& e) {
     fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
+    for (auto& g : w.graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (PartBufs& P : w.parts) {
         fr(P.sel); fr(P.idx_sorted); fr(P.keys); fr(P.keys_sorted); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.w3); fr(P.p3);
         fr(P.tile_sums); fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner);
