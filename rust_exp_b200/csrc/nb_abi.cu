@@ -124,9 +124,7 @@ void nbx_shutdown(void) {
     if (e.mirror) cudaFree(e.mirror);
     if (e.partial) cudaFree(e.partial);
     if (e.force) cudaFree(e.force);
-    if (e.work_counter) cudaFree(e.work_counter);
     if (e.stage_dev) cudaFree(e.stage_dev);
-    if (e.stage_host) cudaFreeHost(e.stage_host);
     for (int p = 0; p < NBX_NUM_PHASES; p++)
         for (int k = 0; k < Engine::kPhaseRing; k++)
             for (int j = 0; j < 2; j++)
@@ -138,9 +136,9 @@ void nbx_shutdown(void) {
     (void)cudaGetLastError();
     // reset to a fresh engine (keep the mutex)
     e.inited = false;
-    e.arena.base = nullptr; e.mirror = nullptr; e.partial = nullptr; e.force = nullptr; e.work_counter = nullptr;
-    e.stage_dev = nullptr; e.stage_host = nullptr; e.own_stream = nullptr; e.stream = nullptr;
-    e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = e.stage_host_cap = 0;
+    e.arena.base = nullptr; e.mirror = nullptr; e.partial = nullptr; e.force = nullptr;
+    e.stage_dev = nullptr; e.own_stream = nullptr; e.stream = nullptr;
+    e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = 0;
     e.lay = ArenaLayout(); e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
     e.cur = 0; e.step_count = 0; e.mode = NBX_MODE_FAST; e.tune = Tuning(); e.ctr = nbx_counters{};
 }

@@ -262,7 +262,6 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     a.i_global_begin = local_begin(e);
     a.n_local = local_count(e);
     a.my_rank = e.rank;
-    a.work_counter = e.work_counter;
     const int I = pick_bodies_per_thread(e);
     const int TI = kComputeThreads * I;
     const int n_itiles = (a.n_local + TI - 1) / TI;

@@ -71,8 +71,6 @@ int try_init(Engine& e, int device) {
     e.num_sms = prop.multiProcessorCount;
     NB_CUDA(cudaStreamCreateWithFlags(&e.own_stream, cudaStreamNonBlocking));
     e.stream = e.own_stream;
-    NB_CUDA(cudaMalloc(&e.work_counter, 64 * sizeof(unsigned int)));
-    NB_CUDA(cudaMemset(e.work_counter, 0, 64 * sizeof(unsigned int)));
     e.inited = true;
     return 0;
 }

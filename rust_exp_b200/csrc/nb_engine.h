@@ -97,8 +97,6 @@ struct AllPairsArgs {
     const uint32_t* flags;
     uint32_t wait_step;
     int my_rank;
-    // scheduling
-    unsigned int* work_counter;
 };
 
 struct Tuning {
@@ -145,12 +143,8 @@ struct Engine {
     size_t partial_cap = 0;  // in float2
     float2* force = nullptr; // exact-mode forces / accelerations [L]
     size_t force_cap = 0;
-    unsigned int* work_counter = nullptr;
-    float* stage_host = nullptr;  // pinned staging for set/get
-    size_t stage_host_cap = 0;
     float* stage_dev = nullptr;
     size_t stage_dev_cap = 0;
-    void* l2_dummy = nullptr;
 
     // counters / timing
     nbx_counters ctr{};
@@ -163,9 +157,6 @@ struct Engine {
     int ev_count[NBX_NUM_PHASES] = {};
     int ev_slot = 0;  // step index within the ring
     float phase_ms[NBX_NUM_PHASES] = {};
-
-    // nccl (dlopen'ed), opaque here
-    void* nccl = nullptr;
 
     // Barnes-Hut workspace, opaque (nb_bh.cu)
     void* bh = nullptr;
@@ -213,7 +204,6 @@ void dist_fill_segments(Engine& e, AllPairsArgs& a);   // seg[] according to tra
 void dist_signal_step_done(Engine& e);                 // publish step_count to peers
 void dist_wait_all(Engine& e, uint32_t step);          // device-side wait for all peers
 void dist_gather_mirror(Engine& e, int buf);           // mirror <- all shards (own kernel or NCCL)
-void dist_barrier_host(Engine& e);
 void dist_shutdown(Engine& e);
 int dist_init(Engine& e, int rank, int world, int max_particles);
 int dist_export(Engine& e, void* out64);

@@ -40,11 +40,6 @@ static void ensure_stage(Engine& e, size_t floats) {
         NB_CUDA(cudaMalloc(&e.stage_dev, floats * sizeof(float)));
         e.stage_dev_cap = floats;
     }
-    if (floats > e.stage_host_cap) {
-        if (e.stage_host) NB_CUDA(cudaFreeHost(e.stage_host));
-        NB_CUDA(cudaMallocHost(&e.stage_host, floats * sizeof(float)));
-        e.stage_host_cap = floats;
-    }
 }
 
 void state_upload_aos(Engine& e, const float* aos5, int n) {
