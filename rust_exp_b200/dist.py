@@ -47,6 +47,28 @@ class ShardLayout:
         return [(rank + q) % self.world for q in range(self.world)]
 
 
+def sfc_partition(cell_counts, nparts: int) -> list[int]:
+    """Cut points of the Barnes-Hut domain split (mirror of nb_bh.cu::bh_forces_partitioned).
+
+    `cell_counts[c]` = bodies in level-5 quadtree cell c, cells in Morton order.  Part g owns the contiguous
+    cell range [cut[g], cut[g+1]); a cut is placed at the first cell whose exclusive prefix count reaches
+    g*N/nparts, so every part gets ~N/nparts bodies up to the granularity of one cell, every cell has
+    exactly one owner, and all ranks compute the same cuts from the same histogram."""
+    n = int(sum(cell_counts))
+    cut = [0]
+    cum = 0
+    g = 1
+    for c, k in enumerate(cell_counts):
+        while g < nparts and cum * nparts >= g * n:
+            cut.append(c)
+            g += 1
+        cum += int(k)
+    while g <= nparts:
+        cut.append(len(cell_counts))
+        g += 1
+    return cut
+
+
 def all_gather_bytes(payload: bytes, group=None) -> list[bytes]:
     import torch.distributed as dist
 

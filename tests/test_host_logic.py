@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from rust_exp_b200 import ic
-from rust_exp_b200.dist import ShardLayout
+from rust_exp_b200.dist import ShardLayout, sfc_partition
 from rust_exp_b200.experiment import RustNBodyExperiment
 
 
@@ -109,3 +109,19 @@ def test_shard_layout_matches_library_arithmetic():
     assert lay.segment_order(2) == [2, 3, 0, 1]
     with pytest.raises(ValueError):
         ShardLayout.for_capacity(10, 9)
+
+
+def test_sfc_partition_properties():
+    rng = np.random.default_rng(3)
+    for nparts in (1, 2, 3, 8):
+        for hist in (rng.integers(0, 5000, 1024), np.r_[np.zeros(1000, int), rng.integers(1, 9, 24)],
+                     np.eye(1, 1024, 517, dtype=int)[0] * 100000, np.zeros(1024, int)):
+            cut = sfc_partition(hist, nparts)
+            assert len(cut) == nparts + 1 and cut[0] == 0 and cut[-1] == 1024
+            assert all(a <= b for a, b in zip(cut, cut[1:]))            # contiguous, every cell owned once
+            n = int(hist.sum())
+            sizes = [int(hist[a:b].sum()) for a, b in zip(cut, cut[1:])]
+            assert sum(sizes) == n
+            if n:
+                # never more than the ideal share plus one cell's worth of bodies
+                assert max(sizes) <= n / nparts + hist.max()
