@@ -56,6 +56,17 @@ def test_exact_matches_oracle_bitwise(fresh, oracle, n, steps, theta, gen):
     assert np.array_equal(bits(g), bits(r))
 
 
+def test_exact_c4_size_262144_one_step_bitwise(fresh, oracle):
+    """configs[3] size in EXACT mode: the serial device build + nested-sum walk reproduce the oracle's step for
+    all 262,144 bodies bit for bit (tree of ~770k nodes, merges included)."""
+    n = 262144
+    s = ic.random_disk(n, seed=4)
+    fresh.set_mode(binding.MODE_EXACT)
+    g = run_gpu(fresh, s, 0.5, 0.01, 1)
+    r = run_ora(oracle, s, 0.5, 0.01, 1, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(bits(g), bits(r))
+
+
 def test_exact_merge_and_coincident_bodies(fresh, oracle):
     s = ic.random_disk(500, seed=8)
     s[1, :2] = s[0, :2] + f32(3e-5)   # too close: merged leaf (rs-src/nbody.rs:249-260)
