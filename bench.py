@@ -432,6 +432,10 @@ def main():
                     "frac": achieved / hbm if achieved else None, "traffic": None, "kernel_ms": trav_ms,
                     "kernel_share_of_step": trav_ms / ms_per_step,
                     "visit_bytes_per_s_cache_served": 32 * vis / world / (trav_ms * 1e-3) if trav_ms > 0 else None,
+                    # the same launch against the FP32 roofline: 10 flop per node visit (2 sub, mul + FMA for d^2, s^2,
+                    # theta^2 d^2, compare, d^2+eps) + 6 per interaction (rcp, m*inv, 2 FMA)
+                    "fp32_tflops": (10 * vis + 6 * inter) / world / (trav_ms * 1e-3) / 1e12 if trav_ms > 0 else None,
+                    "fp32_frac": ((10 * vis + 6 * inter) / world / (trav_ms * 1e-3) / 1e12 / fp32_peak) if trav_ms > 0 else None,
                     "peak_source": ("MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in pk else "fallback 6.65 TB/s") +
                                    "; issue-bound walk over cache-resident nodes (DESIGN.md 4.3)"}
         extra = {"bh_steps_per_s": args.steps / (ms * 1e-3), "bh_interactions_per_s": inter * args.steps / (ms * 1e-3),
