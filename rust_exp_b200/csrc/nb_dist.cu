@@ -122,6 +122,7 @@ static void ensure_mirror(Engine& e) {
         if (e.mirror) NB_CUDA(cudaFree(e.mirror));
         NB_CUDA(cudaMalloc(&e.mirror, need * sizeof(float)));
         e.mirror_cap = need;
+        e.mirror_mass_valid = false;
     }
 }
 
@@ -152,9 +153,10 @@ void dist_gather_mirror(Engine& e, int buf) {
         n->GroupStart();
         n->AllGather(e.arena.x(e.lay, buf), mirror_x(e), L, ncclFloat32, n->comm, e.stream);
         n->AllGather(e.arena.y(e.lay, buf), mirror_y(e), L, ncclFloat32, n->comm, e.stream);
-        n->AllGather(e.arena.m(e.lay), mirror_m(e), L, ncclFloat32, n->comm, e.stream);
+        if (!e.mirror_mass_valid) n->AllGather(e.arena.m(e.lay), mirror_m(e), L, ncclFloat32, n->comm, e.stream);
         ncclResult_t r = n->GroupEnd();
         if (r != 0) fatal(n->GetErrorString ? n->GetErrorString(r) : "ncclAllGather failed", __FILE__, __LINE__);
+        e.mirror_mass_valid = true;
         return;
     }
     dist_wait_all(e, e.step_count);
@@ -169,7 +171,8 @@ void dist_gather_mirror(Engine& e, int buf) {
     dim3 grid(static_cast<unsigned>(min(e.num_sms * 2, (L4 + 255) / 256)), static_cast<unsigned>(e.world));
     gather_kernel<<<grid, 256, 0, e.stream>>>(s, e.world, L4, reinterpret_cast<float4*>(mirror_x(e)),
                                              reinterpret_cast<float4*>(mirror_y(e)),
-                                             reinterpret_cast<float4*>(mirror_m(e)), 1);
+                                             reinterpret_cast<float4*>(mirror_m(e)), e.mirror_mass_valid ? 0 : 1);
+    e.mirror_mass_valid = true;
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
 }

@@ -138,6 +138,7 @@ struct Engine {
     // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies
     float* mirror = nullptr;
     size_t mirror_cap = 0;
+    bool mirror_mass_valid = false;  // masses are constant between set/generate calls: gathered once
     // scratch
     float2* partial = nullptr;
     size_t partial_cap = 0;  // in float2
