@@ -96,6 +96,32 @@ def test_exact_c2_size_65536_one_step(fresh, oracle):
     assert np.array_equal(bits(g), bits(r))
 
 
+def oracle_steps_mt(oracle, s, dt, steps):
+    """K reference steps with the force rows spread over all host cores (rows are independent, so this is
+    bit-identical to ora_step_brute_force; the Euler update below is rs-src/nbody.rs:153-160 in numpy f32)."""
+    r = s.copy()
+    dt = f32(dt)
+    for _ in range(steps):
+        oracle.set_particles(r)
+        f = oracle.brute_forces_rows(0, r.shape[0], nthreads=os.cpu_count() or 1)
+        r[:, 2] = r[:, 2] + (dt * f[:, 0]) / r[:, 4]
+        r[:, 3] = r[:, 3] + (dt * f[:, 1]) / r[:, 4]
+        r[:, 0] = r[:, 0] + dt * r[:, 2]
+        r[:, 1] = r[:, 1] + dt * r[:, 3]
+    return r
+
+
+def test_c2_size_65536_ten_steps_exact_and_fast(fresh, oracle):
+    """configs[1] (65,536-body Plummer), K=10 as SURVEY.md section 8d asks: EXACT bitwise, FAST within 1e-4."""
+    s = ic.plummer_2d(65536, seed=2)
+    r = oracle_steps_mt(oracle, s, 0.01, 10)
+    fresh.set_mode(binding.MODE_EXACT)
+    assert np.array_equal(bits(run_gpu(fresh, s, 0.01, 10)), bits(r))
+    fresh.set_mode(binding.MODE_FAST)
+    g = run_gpu(fresh, s, 0.01, 10)
+    assert rel_err(g, r, [0, 1]) <= POS_TOL and rel_err(g, r, [2, 3]) <= VEL_TOL
+
+
 # ---------------------------------------------------------------- FAST mode: tolerance -------------
 def make(gen, n, seed):
     if gen == "orbits":

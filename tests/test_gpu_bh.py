@@ -159,6 +159,17 @@ def test_c4_size_262144_theta05_one_step(fresh, oracle):
     assert np.quantile(ep, 0.999) <= 1e-6 and np.quantile(ev, 0.999) <= 1e-5   # rounding level for all but flipped walks
 
 
+def test_c4_size_262144_ten_steps_fast(fresh, oracle):
+    """configs[3], K=10 through the graph-replayed FAST step: every body within the stated tolerance of the oracle."""
+    n = 262144
+    s = ic.plummer_2d(n, seed=4)
+    g = run_gpu(fresh, s, 0.5, 0.01, 10)
+    r = run_ora(oracle, s, 0.5, 0.01, 10, nthreads=os.cpu_count() or 1)
+    ext = np.abs(r[:, :2]).max()
+    assert np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max() / ext <= 1e-4
+    assert np.abs(g[:, 2:4].astype(np.float64) - r[:, 2:4]).max() / np.abs(r[:, 2:4]).max() <= 1e-3
+
+
 def test_c5_size_4m_theta075_properties(fresh):
     """configs[4] size (4,194,304 bodies, theta=0.75): size-independent properties -- momentum balance of the
     tree forces (sum m a ~ 0 to within the BH approximation error) and run-to-run determinism."""
