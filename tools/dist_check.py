@@ -33,7 +33,7 @@ def main():
     lib = pkg.load()
     lib.init(lr)
     big = int(os.environ.get("NB_DIST_BIG", 262144))
-    nbdist.wire(lib, max(big, 70000), binding.TRANSPORT_NCCL)  # NCCL comm + IPC arenas; transports switch below
+    nbdist.wire(lib, max(big, 131072), binding.TRANSPORT_NCCL)  # NCCL comm + IPC arenas; transports switch below
     o = oracle.get()
     ok = True
 
@@ -169,7 +169,7 @@ def main():
                pairs_per_s=big * (big - 1) / (float(t.item()) * 1e-3))
     # Barnes-Hut step time, replicated vs partitioned
     nbh = int(os.environ.get("NB_DIST_BH", 1 << 20))
-    if nbh <= max(big, 70000):
+    if nbh <= max(big, 131072):
         sb2 = ic.random_disk(nbh, seed=45)
         for mode, name in ((1, "bh_replicated"), (0, "bh_partitioned")):
             lib.bh_partition(mode)
