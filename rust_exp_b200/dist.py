@@ -1,6 +1,6 @@
 """torch.distributed plumbing for the index-sharded particle set (one process per GPU).
 
-torch.distributed is used ONLY to wire the processes together (exchange the 64-byte CUDA IPC handles of
+torch.distributed is used ONLY to wire the processes together (exchange the 128 bytes of CUDA IPC handles of
 the symmetric arenas, broadcast the NCCL unique id, barrier / max-reduce timings).  The data path of a
 step never goes through it: positions move GPU-to-GPU inside the library's own kernels (bulk-TMA loads
 from peer HBM over NVLink) or, for the baseline transport, the library's own ncclAllGather.
