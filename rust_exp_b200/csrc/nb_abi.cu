@@ -119,6 +119,7 @@ void nbx_shutdown(void) {
     dist_shutdown(e);
     bh_shutdown(e);
     x3_shutdown(e);
+    draw_shutdown();
     if (e.arena.base) cudaFree(e.arena.base);
     if (e.bh_arena) cudaFree(e.bh_arena);
     e.bh_arena = nullptr;

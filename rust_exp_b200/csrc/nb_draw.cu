@@ -84,6 +84,12 @@ static uint32_t rgb_to_abgr32(unsigned r8, unsigned g8, unsigned b8, float facto
 static uint32_t* g_fb_dev = nullptr;
 static size_t g_fb_cap = 0;
 
+void draw_shutdown() {
+    if (g_fb_dev) cudaFree(g_fb_dev);
+    g_fb_dev = nullptr;
+    g_fb_cap = 0;
+}
+
 void draw_to_host(Engine& e, int w, int h, uint32_t* fb) {
     if (w <= 0 || h <= 0) return;
     const size_t px = static_cast<size_t>(w) * static_cast<size_t>(h);

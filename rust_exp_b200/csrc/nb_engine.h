@@ -228,5 +228,6 @@ void x3_shutdown(Engine& e);
 
 // nb_draw.cu
 void draw_to_host(Engine& e, int w, int h, uint32_t* fb);
+void draw_shutdown();
 
 }  // namespace nb

@@ -290,3 +290,27 @@ def test_counters_report_kernel_launches(fresh):
     fresh.synchronize()
     c = fresh.counters()
     assert c["kernel_launches"] == 2 and c["allpairs_pairs"] == 2048 * 2047 and c["steps"] == 1
+
+
+def test_shutdown_and_reinit(oracle):
+    """nbx_shutdown releases everything; the library comes back up on the next call with an empty set."""
+    import rust_exp_b200 as pkg
+
+    L = pkg.load()
+    L.init(0)
+    s = ic.random_disk(3000, seed=3)
+    L.set_particles(s)
+    L.step_barnes_hut(0.5, 0.01, 1)
+    L.draw(64, 64)
+    L.shutdown()
+    assert L.num_particles() == 0
+    L.init(0)
+    L.set_mode(binding.MODE_EXACT)
+    L.set_particles(s)
+    L.step_brute_force(0.01)
+    L.step_barnes_hut(0.5, 0.01, 1)
+    oracle.set_particles(s)
+    oracle.step_brute_force(0.01)
+    oracle.step_barnes_hut(0.5, 0.01, 1)
+    assert np.array_equal(bits(L.get_particles()), bits(oracle.get_particles()))
+    L.set_mode(binding.MODE_FAST)
