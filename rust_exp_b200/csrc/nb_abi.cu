@@ -143,6 +143,10 @@ void nbx_shutdown(void) {
     e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = 0;
     e.lay = ArenaLayout(); e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
     e.cur = 0; e.step_count = 0; e.mode = NBX_MODE_FAST; e.tune = Tuning(); e.ctr = nbx_counters{};
+    e.transport = NBX_TRANSPORT_P2P_DIRECT; e.max_particles = 0; e.mirror_mass_valid = false; e.bh_partition = 0;
+    e.bh_count = false; e.phase_timing = false; e.ev_slot = 0; e.bh_lay = BhArenaLayout();
+    for (int p = 0; p < NBX_NUM_PHASES; p++) e.ev_count[p] = 0;
+    for (int g = 0; g < kMaxRanks; g++) { e.peer[g].base = nullptr; e.bh_peer[g] = nullptr; }
 }
 
 const char* nbx_last_error(void) { return last_error(); }
