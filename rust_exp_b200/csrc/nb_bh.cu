@@ -310,10 +310,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const double* 
 // exists exactly for l in (dcap(i-1), dcap(i)], where dcap is delta capped (a) at kLevels-1 and (b), for
 // pairs inside a chain of mutually close bodies, below the first level at which the chain is alone in
 // its cell -- that cell becomes a merged leaf.  A prefix sum over count(i) = max(0, dcap(i)-dcap(i-1)) numbers
-// the interior nodes; node k owns the 4-slot child block [4+4k, 4+4k+4) (64-byte aligned float4 records),
-// and every node's record lives in its parent's block (the root in slot 0).  One thread per body then emits
-// the nodes that start at it: range end and child boundaries by binary search on the keys, mass/COM from the
-// f64 prefix sums, cell bounds by replaying the key bits through the reference's midpoint recursion.
+// the interior nodes; node k owns child block 1+k (one 64-byte SoA record x[4] y[4] m[4] s[4] plus four child
+// block indices), and every node's record lives in its parent's block (the root in slot 0 of block 0).  One
+// thread per interior node then emits its block: range end and child boundaries by binary search on the keys,
+// mass/COM from the f64 prefix sums, cell bounds by replaying the key bits through the reference's midpoint
+// recursion.
 __device__ __forceinline__ int lower_bound_quadrant(const unsigned long long* __restrict__ keys, int lo, int hi,
                                                     int shift, unsigned q) {
     // first position in [lo,hi) whose 2 key bits at `shift` are >= q (keys are sorted)
