@@ -115,6 +115,11 @@ void nbx_get_counters(nbx_counters *out);
 void nbx_reset_counters(void);
 int32_t nbx_bh_count_interactions(int32_t enable);
 
+/* Parity aid: the quadtree of the most recent FAST Barnes-Hut call in DFS pre-order (children UL,UR,LL,LR),
+ * 9 floats per node {x1,y1,x2,y2, px,py,m, has_children, depth} -- the layout the CPU oracle dumps -- into a HOST
+ * array holding `cap` nodes.  Returns the number of nodes of the tree (may exceed cap), <0 on error. */
+int32_t nbx_bh_flatten(float *out9, int32_t cap);
+
 /* Domain partitioning of the FAST Barnes-Hut step: 0 = automatic (one part per GPU when
  * sharded over several GPUs and the set has >= 65,536 bodies; one tree otherwise), 1 = always one replicated
  * tree, 2..8 on a single GPU = that many "virtual ranks" (exercises the partitioned code path for tests). */

@@ -40,6 +40,7 @@ SYMBOLS = {
     "nbx_get_counters": (None, [vp]),
     "nbx_reset_counters": (None, []),
     "nbx_bh_count_interactions": (i32, [i32]),
+    "nbx_bh_flatten": (i32, [vp, i32]),
     "nbx_bh_partition": (i32, [i32]),
     "nbx_phase_timing": (i32, [i32]),
     "nbx_get_phase_ms": (i32, [vp]),
@@ -179,6 +180,15 @@ class NBodyLib:
 
     def bh_count_interactions(self, on: bool) -> None:
         self.L.nbx_bh_count_interactions(1 if on else 0)
+
+    def bh_flatten(self) -> np.ndarray:
+        n = int(self.L.nbx_bh_flatten(None, 0))
+        if n < 0:
+            raise RuntimeError(f"nbx_bh_flatten failed ({n})")
+        out = np.empty((n, 9), dtype=np.float32)
+        got = int(self.L.nbx_bh_flatten(out.ctypes.data, n))
+        assert got == n, (got, n)
+        return out
 
     def bh_partition(self, parts: int) -> None:
         self._chk(self.L.nbx_bh_partition(parts), "nbx_bh_partition")

@@ -223,6 +223,13 @@ int32_t nbx_bh_count_interactions(int32_t enable) {
     return 0;
 }
 
+int32_t nbx_bh_flatten(float* out9, int32_t cap) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    return bh_flatten(e, out9, cap);
+}
+
 int32_t nbx_bh_partition(int32_t parts) {
     NB_LOCK();
     if (parts < 0 || parts > kMaxRanks) {

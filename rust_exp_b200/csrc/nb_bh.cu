@@ -101,6 +101,18 @@ struct TopBufs {
     int* hist_host = nullptr;     // pinned
 };
 
+// Block index space: (part << shift) | block.  One tree: shift = 31, part 0.  Partitioned trees: part g < world
+// is rank g's subtree forest (possibly in a PEER GPU's memory, walked in place over NVLink), part kMaxRanks is
+// the small shared top tree.  Accelerations are scattered to the rank that owns the body's index shard.
+struct TreeTable {
+    const float4* blk[kMaxRanks + 1];
+    const int4* cblk[kMaxRanks + 1];
+    float2* acc[kMaxRanks];
+    int shift;
+    unsigned root;
+    int shard_len;     // L: owner of body i is i / L, its slot i % L
+};
+
 struct PeerU32 { uint32_t* p[kMaxRanks]; };
 
 struct BhWork {
@@ -145,6 +157,8 @@ struct BhWork {
     TopBufs top;
     uint32_t bh_epoch = 0;
     float2* acc_src = nullptr;       // where this step's per-local-body accelerations ended up
+    TreeTable last_tt{};             // the tree of the most recent FAST step (for nbx_bh_flatten)
+    int last_nparts = 0;             // 0 = no FAST tree yet, 1 = single tree, >1 = partitioned
     bool last_partitioned = false;
 };
 
@@ -585,18 +599,6 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 // child to be opened; only children that some lane must open are pushed, with that lane mask.  Every body
 // therefore evaluates exactly the reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and
 // the body's own leaf (d = 0, :365) need no test: their contribution is an exact zero because EPS > 0.
-// Block index space: (part << shift) | block.  One tree: shift = 31, part 0.  Partitioned trees: part g < world
-// is rank g's subtree forest (possibly in a PEER GPU's memory, walked in place over NVLink), part kMaxRanks is
-// the small shared top tree.  Accelerations are scattered to the rank that owns the body's index shard.
-struct TreeTable {
-    const float4* blk[kMaxRanks + 1];
-    const int4* cblk[kMaxRanks + 1];
-    float2* acc[kMaxRanks];
-    int shift;
-    unsigned root;
-    int shard_len;     // L: owner of body i is i / L, its slot i % L
-};
-
 template <bool COUNT>
 __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
@@ -929,6 +931,7 @@ static void bh_forces(Engine& e, float theta) {
             for (int g = 0; g < kMaxRanks; g++) tt.acc[g] = w.acc;
             tt.acc[e.rank] = w.acc;
             tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
+            w.last_tt = tt; w.last_nparts = 1;
             launch_traverse(e, tt, w.sx, w.sy, w.idx_sorted, mine, n_list, theta, w.status);
         }
     }
@@ -1338,6 +1341,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     }
     (void)nl;
     w.last_partitioned = true;
+    w.last_tt = tt; w.last_nparts = nparts;
     NB_CUDA(cudaGetLastError());
 }
 
@@ -1438,6 +1442,70 @@ void bh_accelerations(Engine& e, float theta, float2* out) {
     e.step_count++;
     dist_signal_step_done(e);
     check_status(e, w, true);
+}
+
+// Debug / parity aid: the FAST tree of the most recent Barnes-Hut call in the oracle's flatten format (DFS
+// pre-order, children in index order; 9 floats per node: x1,y1,x2,y2,px,py,m,has_children,depth), so that tests
+// can compare it with the reference tree node by node.  Walks downloaded copies of the block arrays on the host.
+int bh_flatten(Engine& e, float* out9, int cap) {
+    if (!e.bh) return 0;
+    BhWork& w = work(e);
+    if (w.last_nparts == 0) return 0;
+    check_status(e, w, true);
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    const BhStatus h = *w.status_host;
+    const TreeTable& tt = w.last_tt;
+    const int nslots = kMaxRanks + 1;
+    std::vector<std::vector<float4>> blk(nslots);
+    std::vector<std::vector<int4>> cblk(nslots);
+    auto fetch = [&](int part, size_t nblocks) {
+        if (!tt.blk[part] || nblocks == 0) return;
+        blk[part].resize(4 * nblocks);
+        cblk[part].resize(nblocks);
+        NB_CUDA(cudaMemcpy(blk[part].data(), tt.blk[part], sizeof(float4) * 4 * nblocks, cudaMemcpyDeviceToHost));
+        NB_CUDA(cudaMemcpy(cblk[part].data(), tt.cblk[part], sizeof(int4) * nblocks, cudaMemcpyDeviceToHost));
+    };
+    if (w.last_nparts == 1) {
+        fetch(0, static_cast<size_t>(h.n_interior) + 1);
+    } else {
+        if (e.dist && e.world > 1) return -1;   // peers' arrays are not fetched here: single-process (virtual ranks) only
+        for (int r = 0; r < w.last_nparts; r++) fetch(r, static_cast<size_t>(w.parts[r].cap_blocks));
+        fetch(kMaxRanks, kTopNodes + 1);
+    }
+    auto ord2f_h = [](int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; };
+    struct Item { unsigned blockidx; int slot; float x1, y1, x2, y2; int depth; };
+    std::vector<Item> stack;
+    stack.push_back(Item{tt.root, 0, ord2f_h(h.aabb_enc[0]), ord2f_h(h.aabb_enc[1]), ord2f_h(h.aabb_enc[2]), ord2f_h(h.aabb_enc[3]), 0});
+    int count = 0;
+    const unsigned mask = tt.shift >= 31 ? 0x7fffffffu : ((1u << tt.shift) - 1u);
+    while (!stack.empty()) {
+        const Item it = stack.back();
+        stack.pop_back();
+        const unsigned part = tt.shift >= 31 ? 0u : (it.blockidx >> tt.shift), bi = it.blockidx & mask;
+        if (part >= static_cast<unsigned>(nslots) || 4 * static_cast<size_t>(bi) + 3 >= blk[part].size()) return -2;
+        const float* X = reinterpret_cast<const float*>(&blk[part][4 * bi + 0]);
+        const float* Y = reinterpret_cast<const float*>(&blk[part][4 * bi + 1]);
+        const float* M = reinterpret_cast<const float*>(&blk[part][4 * bi + 2]);
+        const float* S = reinterpret_cast<const float*>(&blk[part][4 * bi + 3]);
+        const int* C = reinterpret_cast<const int*>(&cblk[part][bi]);
+        const bool interior = S[it.slot] >= 0.0f;
+        if (count < cap) {
+            float* r = out9 + 9 * static_cast<size_t>(count);
+            r[0] = it.x1; r[1] = it.y1; r[2] = it.x2; r[3] = it.y2;
+            r[4] = X[it.slot]; r[5] = Y[it.slot]; r[6] = M[it.slot];
+            r[7] = interior ? 1.0f : 0.0f; r[8] = static_cast<float>(it.depth);
+        }
+        count++;
+        if (interior) {
+            const float cx = (it.x1 + it.x2) * 0.5f, cy = (it.y1 + it.y2) * 0.5f;   // rs-src/nbody.rs:289-300
+            const Item ch[4] = {Item{static_cast<unsigned>(C[it.slot]), 0, it.x1, cy, cx, it.y2, it.depth + 1},
+                                Item{static_cast<unsigned>(C[it.slot]), 1, cx, cy, it.x2, it.y2, it.depth + 1},
+                                Item{static_cast<unsigned>(C[it.slot]), 2, it.x1, it.y1, cx, cy, it.depth + 1},
+                                Item{static_cast<unsigned>(C[it.slot]), 3, cx, it.y1, it.x2, cy, it.depth + 1}};
+            for (int q = 3; q >= 0; q--) stack.push_back(ch[q]);
+        }
+    }
+    return count;
 }
 
 void bh_shutdown(Engine& e) {

@@ -216,6 +216,7 @@ int dist_nccl_init(Engine& e, const void* id128);
 void bh_step(Engine& e, float theta, float dt);
 void bh_accelerations(Engine& e, float theta, float2* out);
 void bh_shutdown(Engine& e);
+int bh_flatten(Engine& e, float* out9, int cap);   // FAST tree of the last BH call, oracle flatten format
 void bh_poll(Engine& e);   // fold the last Barnes-Hut step's status/counters in (synchronises)
 
 // nb_3d.cu

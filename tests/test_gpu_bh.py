@@ -184,6 +184,34 @@ def test_c5_size_4m_theta075_properties(fresh):
     assert np.array_equal(bits(a.astype(np.float32)), bits(b))
 
 
+@pytest.mark.parametrize("n,gen,parts", [(4096, "disk", 1), (65536, "plummer", 1), (50000, "orbits", 1), (65536, "disk", 4),
+                                         (100000, "plummer", 8)])
+def test_fast_tree_equals_reference_tree_node_by_node(fresh, oracle, n, gen, parts, monkeypatch):
+    """The FAST (sort-based) tree dumped in the oracle's DFS format: same nodes in the same order, cell boxes bit
+    for bit, leaves bit for bit, interior mass/COM to rounding (f64 prefix sums vs the f32 running mean)."""
+    monkeypatch.setenv("NB_BH_PARTS_MIN_N", "0")
+    s = ic.stable_orbits(n, 0.5, 30.0, seed=4) if gen == "orbits" else \
+        (ic.random_disk(n, seed=4) if gen == "disk" else ic.plummer_2d(n, seed=4))
+    fresh.bh_partition(parts)
+    fresh.set_particles(s)
+    fresh.bh_accelerations(0.5)
+    t = fresh.bh_flatten()
+    oracle.set_particles(s)
+    oracle.bh_build()
+    r = oracle.bh_flatten()
+    assert t.shape == r.shape
+    assert np.array_equal(t[:, 7:9], r[:, 7:9])                       # same topology, same DFS order
+    assert np.array_equal(bits(t[:, 0:4]), bits(r[:, 0:4]))           # cell boxes bit for bit
+    leaf = r[:, 7] == 0
+    single = leaf & (r[:, 6] > 0)
+    # leaves holding one body are exact copies; merged leaves (rare) agree to rounding
+    exact = np.all(bits(t[single][:, 4:7]) == bits(r[single][:, 4:7]), axis=1)
+    assert exact.mean() >= 0.999
+    ext = np.abs(s[:, :2]).max()
+    assert np.abs(t[:, 4:6].astype(np.float64) - r[:, 4:6]).max() / ext <= 2e-6
+    assert np.abs(t[:, 6].astype(np.float64) - r[:, 6]).max() / r[:, 6].max() <= 1e-6
+
+
 # ------------------------------------------------------------------ domain-partitioned build -----------
 @pytest.mark.parametrize("n,theta,gen,parts", [(65536, 0.5, "disk", 2), (65536, 0.75, "plummer", 8), (100000, 0.5, "orbits", 4),
                                                (262144, 0.5, "disk", 8)])
