@@ -207,15 +207,18 @@ def test_fast_tree_equals_reference_tree_node_by_node(fresh, oracle, n, gen, par
     # leaves holding one body are exact copies; merged leaves (rare) agree to rounding
     exact = np.all(bits(t[single][:, 4:7]) == bits(r[single][:, 4:7]), axis=1)
     assert exact.mean() >= 0.999
-    # interior nodes: the reference's COM / mass are f32 running sums over up to n insertions (rounding random
-    # walk ~ sqrt(n) * 6e-8 ~ 2e-5 at the root for 100k bodies); the FAST tree's are f64 prefix sums rounded once
+    # Interior nodes: the reference's mass / COM are f32 running sums over up to n insertions.  For equal masses
+    # the rounding of every `m += dm` has the same sign within a binade, so the error grows LINEARLY (measured:
+    # ~1e-3 relative at the root of a 65k-body equal-mass set); the FAST tree's are f64 prefix sums rounded once.
     ext = np.abs(s[:, :2]).max()
-    assert np.abs(t[:, 4:6].astype(np.float64) - r[:, 4:6]).max() / ext <= 1e-4
-    assert np.abs(t[:, 6].astype(np.float64) - r[:, 6]).max() / r[:, 6].max() <= 1e-4
+    assert np.abs(t[:, 4:6].astype(np.float64) - r[:, 4:6]).max() / ext <= 2e-3
+    assert np.abs(t[:, 6].astype(np.float64) - r[:, 6]).max() / r[:, 6].max() <= 5e-3
     # ...and against an f64 evaluation the FAST root is the more accurate of the two
     m64, x64 = s[:, 4].astype(np.float64), s[:, 0].astype(np.float64)
-    com_x = (m64 * x64).sum() / m64.sum()
+    com_x, mass = (m64 * x64).sum() / m64.sum(), m64.sum()
     assert abs(t[0, 4] - com_x) <= abs(r[0, 4] - com_x) + 1e-6 * ext
+    assert abs(t[0, 6] - mass) <= abs(r[0, 6] - mass) + 1e-6 * mass
+    assert abs(t[0, 6] - mass) <= 1e-6 * mass
 
 
 # ------------------------------------------------------------------ domain-partitioned build -----------
