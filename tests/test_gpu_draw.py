@@ -38,3 +38,17 @@ def test_draw_saturates(fresh, oracle):
     a = fresh.draw(128, 128)
     assert np.array_equal(a, oracle.draw(128, 128))
     assert (a == 0x00A6FFFF).any() or (a & 0xFF).max() == 255
+
+
+def test_draw_tail_octants_and_boundaries(fresh, oracle):
+    """Every octant plus velocities exactly on the octant boundaries (multiples of 45 degrees) and zero velocity."""
+    v = [(1, 0), (1, 1), (0, 1), (-1, 1), (-1, 0), (-1, -1), (0, -1), (1, -1), (0, 0), (1e-30, -1e-30), (3, 3.0000002),
+         (1.0, 0.1), (-0.1, 1.0), (-1.0, -0.1), (0.1, -1.0), (2.5, -2.5), (-7, 7)]
+    s = np.zeros((len(v), 5), dtype=np.float32)
+    s[:, 0] = np.linspace(-40, 40, len(v))
+    s[:, 1] = np.linspace(-30, 30, len(v))
+    s[:, 2:4] = np.array(v, dtype=np.float32)
+    s[:, 4] = 1.0
+    fresh.set_particles(s)
+    oracle.set_particles(s)
+    assert np.array_equal(fresh.draw(200, 150), oracle.draw(200, 150))

@@ -212,3 +212,20 @@ def test_edge_cases_empty_and_single(oracle):
     oracle.set_particles(one)
     oracle.step_barnes_hut(0.5, 0.1, 1)
     assert np.array_equal(bits(oracle.get_particles()), bits(q))
+
+
+def test_draw_tail_octants(oracle):
+    """rs-src/nbody.rs:541-555: the 1-pixel tail lies opposite to the velocity, in one of 8 octants; octant k covers
+    angles [k*45deg, (k+1)*45deg) because the reference TRUNCATES 8*angle/2pi+8 (no rounding to nearest)."""
+    cases = {  # velocity -> (dx, dy) of the tail pixel relative to the body pixel
+        (1.0, 0.1): (-1, 0), (1.0, 1.1): (-1, -1), (-0.1, 1.0): (0, -1), (-1.0, 0.9): (1, -1),
+        (-1.0, -0.1): (1, 0), (-1.0, -1.1): (1, 1), (0.1, -1.0): (0, 1), (1.0, -0.9): (-1, 1),
+        (1.0, -0.1): (-1, 1),   # angle just below 0 -> 8*a/2pi+8 just below 8 -> octant 7 (SE)
+    }
+    for (vx, vy), (dx, dy) in cases.items():
+        oracle.set_particles(np.array([[10.0, 20.0, vx, vy, 1.0]], dtype=f32))
+        fb = oracle.draw(100, 100)
+        bx, by = 60, 70
+        assert fb[by, bx] == 0x0027404C, (vx, vy)
+        assert fb[by + dy, bx + dx] == 0x0020353F, (vx, vy, dx, dy)
+        assert (fb != 0).sum() == 2 + 5
