@@ -43,3 +43,43 @@ def test_gpu_arm_fails_loudly_without_gpu():
     p = run("--steps", "1", timeout=120)
     assert p.returncode != 0
     assert "no CPU path" in (p.stderr + p.stdout) or "no CUDA device" in (p.stderr + p.stdout)
+
+
+def test_clock_sampler_parses_nvidia_smi_rows():
+    """bench.py's clocks record: median SM clock under load, max clock, active throttle reasons in the timed window."""
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    cs = b.ClockSampler(0)
+
+    class P:
+        def terminate(self):
+            pass
+
+    cs.proc = P()
+    t = time.perf_counter()
+    cs.rows = [
+        (t - 5.0, "120, 1965, 140.0, Not Active, Not Active, Not Active, Not Active"),     # before the window: ignored
+        (t + 0.1, "1965, 1965, 640.5, Not Active, Not Active, Not Active, Not Active"),
+        (t + 0.2, "1950, 1965, 655.0, Not Active, Not Active, Not Active, Active"),
+        (t + 0.3, "1965, 1965, 650.0, Not Active, Not Active, Not Active, Not Active"),
+    ]
+    out = cs.stop(t, t + 0.4)
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"] and abs(out["power_w_max"] - 655.0) < 1e-6
+
+
+def test_workload_table_matches_baseline_configs():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    w = b.WORKLOADS
+    assert w["c2"]["n"] == 65536 and w["c3"]["n"] == 1048576 and w["c4"]["n"] == 262144 and w["c5"]["n"] == 4194304
+    assert w["c4"]["theta"] == 0.5 and w["c5"]["theta"] == 0.75 and b.FLOP_PER_PAIR == 12
+    cfg = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    assert "65,536" in cfg[1] and "1,048,576" in cfg[2] and "262,144" in cfg[3] and "4,194,304" in cfg[4]
