@@ -54,12 +54,20 @@ void nb_stable_orbits(int32_t num_particles, float rmin, float rmax) {
     replace_set_end(e);
 }
 
+// NB_SYNC_STEPS=1 makes every step call return only when the GPU has finished it, like the reference's
+// synchronous CPU call -- for hosts that put a wall-clock timer around the step (hs-src/RustNBodyExperiment.hs:55-57).
+static bool sync_steps() {
+    static const bool v = [] { const char* s = getenv("NB_SYNC_STEPS"); return s && atoi(s) != 0; }();
+    return v;
+}
+
 // rs-src/nbody.rs:106-162
 void nb_step_brute_force(float dt) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
     step_brute_force(e, dt);
+    if (sync_steps()) NB_CUDA(cudaStreamSynchronize(e.stream));
 }
 
 // rs-src/nbody.rs:186-480 -- theta first
@@ -69,10 +77,11 @@ void nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
     ensure_init(e);
     if (theta == 0.0f) {  // rs-src/nbody.rs:197-200 (before nthreads is ever used)
         step_brute_force(e, dt);
-        return;
+    } else {
+        if (nthreads <= 0) fatal("nb_step_barnes_hut: nthreads must be >= 1 (the reference divides by it)", __FILE__, __LINE__);
+        bh_step(e, theta, dt);
     }
-    if (nthreads <= 0) fatal("nb_step_barnes_hut: nthreads must be >= 1 (the reference divides by it)", __FILE__, __LINE__);
-    bh_step(e, theta, dt);
+    if (sync_steps()) NB_CUDA(cudaStreamSynchronize(e.stream));
 }
 
 // rs-src/nbody.rs:482-583
