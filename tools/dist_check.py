@@ -141,7 +141,22 @@ def main():
     report("bh_partitioned_5_steps_vs_oracle", err <= 1e-4, rel_pos_err=err)
     lib.bh_count_interactions(False)
 
+    # ---- device-side generators when sharded: counter-based RNG keyed by the GLOBAL body index ----------
+    lib.seed(77)
+    lib.stable_orbits(50000, 0.5, 30.0)
+    ga = lib.get_particles()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bits(ga).tobytes())
+    rr = np.hypot(ga[1:, 0], ga[1:, 1])
+    report("generators_sharded", all(a == gathered[0] for a in gathered) and tuple(ga[0]) == (0, 0, 0, 0, 1000.0)
+           and rr.min() >= 0.5 - 1e-3 and rr.max() <= 30.0 + 1e-3 and lib.num_particles() == 50000)
+    lib.step_barnes_hut(0.85, 0.01, 1)   # the reference's default frame: step, then draw
+    fb0 = lib.draw(160, 120)
+    report("default_scene_frame_sharded", fb0[60, 80] == 0x00FF00FF and (fb0 != 0).sum() > 1000)
+    lib.set_particles(sp[:20000])
+
     fb = lib.draw(128, 96)
+    g = lib.get_particles()
     o.set_particles(g)
     report("draw_sharded", np.array_equal(fb, o.draw(128, 96)))
 
