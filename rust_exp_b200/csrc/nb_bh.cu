@@ -113,6 +113,7 @@ struct TreeTable {
     int shard_len;     // L: owner of body i is i / L, its slot i % L
 };
 
+struct NodeInfo { int first, end, blk, slot_level; };   // slot_level = slot | (level << 8); own record = nblk[blk].slot
 struct PeerU32 { uint32_t* p[kMaxRanks]; };
 
 struct BhWork {
@@ -134,6 +135,11 @@ struct BhWork {
     signed char *delta = nullptr, *dcap = nullptr;
     unsigned char* close = nullptr;
     int *count = nullptr, *base = nullptr, *owner = nullptr;
+    // EXACT parallel build
+    unsigned *xk = nullptr, *xk_sorted = nullptr;
+    int *xorder = nullptr, *idx_l = nullptr, *xflags = nullptr, *xflags_host = nullptr;
+    unsigned long long* lk_tmp = nullptr;
+    NodeInfo* info = nullptr;
     BhStatus* status = nullptr;
     BhStatus* status_host = nullptr;
     float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
@@ -397,6 +403,7 @@ struct BuildArgs {
     int n, cap_interior;
     unsigned part_off;   // added to every child block index (global block index space of partitioned trees)
     int cut_level;       // partitioned build: interior nodes at levels >= cut_level are counted in n_deep
+    struct NodeInfo* info;   // EXACT parallel build: per interior node its body range, level and own record slot
 };
 
 __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
@@ -476,6 +483,10 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
         const int f[5] = {i, e1, e2, e3, end};
         const float cx = __fmul_rn(__fadd_rn(x1, x2), 0.5f);
         const int blk = 1 + id;   // block 0 holds the root (slot 0; slots 1..3 are empty leaves)
+        if (a.info) {   // range + level of this node; its own record slot is filled in by its parent below
+            a.info[id].first = i; a.info[id].end = end;
+            if (l == 0) { a.info[id].blk = 0; a.info[id].slot_level = 0; }
+        }
         if (l == 0) {   // the root's own record
             const double M = a.p3[a.n] - a.p3[0];
             a.nblk[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M), 0.f, 0.f, 0.f);
@@ -507,6 +518,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
                     rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
                     chp[q] = static_cast<int>(a.part_off) + 1 + cid;
+                    if (a.info) { a.info[cid].blk = blk; a.info[cid].slot_level = q | ((l + 1) << 8); }
                 } else {
                     float bx = 0.f, by = 0.f, bm = 0.f;
                     for (int k = 0; k < cnt; k++) add_mass_ref(bx, by, bm, a.sx[first + k], a.sy[first + k], a.sm[first + k]);
@@ -747,6 +759,122 @@ __global__ void bh_traverse_exact_kernel(const float4* __restrict__ ndata, const
     force_out[il] = make_float2(rx, ry);
 }
 
+// ---- EXACT build, parallel variant (merge-free sets) ---------------------------------------------------------
+// If no two bodies are closer than EPS in both axes, Node::insert never merges (rs-src/nbody.rs:249-260), the
+// reference tree is the pure refinement tree -- exactly what the sort-based build produces -- and an interior
+// node's (px,py,m) is add_mass folded over the bodies of its subtree in ascending particle index
+// (rs-src/nbody.rs:234-236,303-320).  So: sort-based topology, then per level one STABLE sort of the body
+// indices by the level's key prefix (index order survives inside every cell) and one thread per interior node
+// folding its bodies sequentially with the reference's rounding.  Any too-close pair (or a pair that shares all
+// 24 key levels) sends the step to the serial build instead, which reproduces merges bit for bit.
+__global__ void bh_xkeys_kernel(const float* __restrict__ x, int n, unsigned* __restrict__ xk, int* __restrict__ idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xk[i] = static_cast<unsigned>(f2ord(x[i])) ^ 0x80000000u;   // order-preserving unsigned key
+    idx[i] = i;
+}
+
+// bodies sorted by x: any later body within EPS in x and in y?  (window capped: a pathological pile-up counts as "close")
+__global__ void bh_close_scan_kernel(const int* __restrict__ order, const float* __restrict__ x, const float* __restrict__ y,
+                                     int n, int* __restrict__ flag) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int i = order[p];
+    const float xi = x[i], yi = y[i];
+    for (int q = p + 1; q < n; q++) {
+        const int j = order[q];
+        if (!(fabsf(__fsub_rn(x[j], xi)) < kEps)) break;
+        if (fabsf(__fsub_rn(y[j], yi)) < kEps || q - p > 4096) { *flag = 1; return; }
+    }
+}
+
+// flag[1] = some pair shares all key levels (the reference would split deeper); flag[2] = deepest interior level
+__global__ void bh_maxdelta_kernel(const signed char* __restrict__ delta, const signed char* __restrict__ dcap, int n,
+                                   int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (delta[i] >= kLevels) flag[1] = 1;
+    atomicMax(&flag[2], static_cast<int>(dcap[i]));
+}
+
+__global__ void bh_exact_fold_kernel(int level, const NodeInfo* __restrict__ info, const BhStatus* st,
+                                     const int* __restrict__ idx_l, const float* __restrict__ x, const float* __restrict__ y,
+                                     const float* __restrict__ m, float4* nblk) {
+    const int T = st->n_interior;
+    float* nf = reinterpret_cast<float*>(nblk);
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < T; id += gridDim.x * blockDim.x) {
+        const NodeInfo ni = info[id];
+        if ((ni.slot_level >> 8) != level) continue;
+        float px = 0.f, py = 0.f, mm = 0.f;
+        for (int p = ni.first; p < ni.end; p++) {
+            const int j = idx_l ? idx_l[p] : p;
+            add_mass_ref(px, py, mm, x[j], y[j], m[j]);
+        }
+        const int slot = ni.slot_level & 3;
+        nf[(4 * static_cast<size_t>(ni.blk) + 0) * 4 + slot] = px;
+        nf[(4 * static_cast<size_t>(ni.blk) + 1) * 4 + slot] = py;
+        nf[(4 * static_cast<size_t>(ni.blk) + 2) * 4 + slot] = mm;
+    }
+}
+
+// rs-src/nbody.rs:333-377 on the block-SoA tree, nested summation order preserved
+struct FrameB { unsigned blk; int slot; int next; unsigned cb; float fx, fy; };
+
+__global__ void bh_traverse_exact_blk_kernel(const float4* __restrict__ nblk, const int4* __restrict__ ncblk,
+                                             const float* __restrict__ x, const float* __restrict__ y,
+                                             const float* __restrict__ m, int i_begin, int n_local, float theta,
+                                             float2* __restrict__ force_out) {
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= n_local) return;
+    const float px = x[i_begin + il], py = y[i_begin + il], pm = m[i_begin + il];
+    const float* nf = reinterpret_cast<const float*>(nblk);
+    const int* cf = reinterpret_cast<const int*>(ncblk);
+    FrameB st[64];
+    int sp = 0;
+    st[0] = FrameB{0u, 0, -1, 0u, 0.f, 0.f};
+    float rx = 0.f, ry = 0.f;
+    while (sp >= 0) {
+        FrameB& f = st[sp];
+        if (f.next < 0) {
+            const size_t b4 = 4 * static_cast<size_t>(f.blk);
+            const float nx = nf[(b4 + 0) * 4 + f.slot], ny = nf[(b4 + 1) * 4 + f.slot];
+            const float nm = nf[(b4 + 2) * 4 + f.slot], ns = nf[(b4 + 3) * 4 + f.slot];
+            if (ns >= 0.f) {  // interior
+                const float dx = __fsub_rn(nx, px), dy = __fsub_rn(ny, py);
+                const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));   // :344
+                if (__fdiv_rn(ns, d) < theta) {                                             // :345
+                    force_ref(px, py, pm, nx, ny, nm, rx, ry);
+                    sp--;
+                } else {
+                    f.fx = 0.f; f.fy = 0.f;
+                    f.cb = static_cast<unsigned>(cf[4 * static_cast<size_t>(f.blk) + f.slot]);
+                    f.next = 1;
+                    st[sp + 1] = FrameB{f.cb, 0, -1, 0u, 0.f, 0.f};
+                    sp++;
+                    continue;
+                }
+            } else {  // leaf :363-374
+                if ((nx == px && ny == py) || nm == 0.0f) { rx = 0.f; ry = 0.f; }
+                else force_ref(px, py, pm, nx, ny, nm, rx, ry);
+                sp--;
+            }
+        } else {
+            f.fx = __fadd_rn(f.fx, rx);   // :358-359
+            f.fy = __fadd_rn(f.fy, ry);
+            if (f.next < 4) {
+                st[sp + 1] = FrameB{f.cb, f.next, -1, 0u, 0.f, 0.f};
+                f.next++;
+                sp++;
+                continue;
+            }
+            rx = f.fx; ry = f.fy;
+            sp--;
+        }
+        if (sp < 0) break;
+    }
+    force_out[il] = make_float2(rx, ry);
+}
+
 // mine[] = sorted positions whose body index lies in [b, b+c)
 struct InRange {
     const int* idx_sorted;
@@ -792,7 +920,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         auto fr = [](void* p) { if (p) cudaFree(p); };
         fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp);
+        fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.xk); fr(w.xk_sorted); fr(w.xorder); fr(w.idx_l); fr(w.lk_tmp); fr(w.info); fr(w.cub_tmp);
         const size_t N = static_cast<size_t>(n);
         NB_CUDA(cudaMalloc(&w.keys, N * 8)); NB_CUDA(cudaMalloc(&w.keys_sorted, N * 8));
         NB_CUDA(cudaMalloc(&w.idx, N * 4)); NB_CUDA(cudaMalloc(&w.idx_sorted, N * 4)); NB_CUDA(cudaMalloc(&w.mine, N * 4));
@@ -807,6 +935,9 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         NB_CUDA(cudaMalloc(&w.delta, N)); NB_CUDA(cudaMalloc(&w.dcap, N)); NB_CUDA(cudaMalloc(&w.close, N));
         NB_CUDA(cudaMalloc(&w.count, N * 4)); NB_CUDA(cudaMalloc(&w.base, N * 4));
         NB_CUDA(cudaMalloc(&w.owner, sizeof(int) * (w.cap_nodes / 4)));
+        NB_CUDA(cudaMalloc(&w.xk, N * 4)); NB_CUDA(cudaMalloc(&w.xk_sorted, N * 4));
+        NB_CUDA(cudaMalloc(&w.xorder, N * 4)); NB_CUDA(cudaMalloc(&w.idx_l, N * 4)); NB_CUDA(cudaMalloc(&w.lk_tmp, N * 8));
+        NB_CUDA(cudaMalloc(&w.info, sizeof(NodeInfo) * (w.cap_nodes / 4)));
         NB_CUDA(cudaMalloc(&w.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
         size_t b1 = 0, b2 = 0, b3 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, e.stream);
@@ -824,6 +955,8 @@ static void ensure_status(BhWork& w) {
         NB_CUDA(cudaMallocHost(&w.status_host, sizeof(BhStatus)));
         memset(w.status_host, 0, sizeof(BhStatus));
         NB_CUDA(cudaEventCreateWithFlags(&w.status_ev, cudaEventDisableTiming));
+        NB_CUDA(cudaMalloc(&w.xflags, 4 * sizeof(int)));
+        NB_CUDA(cudaMallocHost(&w.xflags_host, 4 * sizeof(int)));
     }
 }
 
@@ -835,6 +968,44 @@ static GlobalPos global_positions(Engine& e) {
     dist_gather_mirror(e, e.cur);
     const size_t GL = static_cast<size_t>(e.world) * e.lay.L;
     return GlobalPos{e.mirror, e.mirror + GL, e.mirror + 2 * GL};
+}
+
+// keys -> sort -> gather/scan -> single-pass build of ONE tree over all n bodies (nblk / ncblk)
+static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, NodeInfo* info) {
+    cudaStream_t s = e.stream;
+    const int T = 256, G = (n + T - 1) / T;
+        {
+        PhaseScope ps(e, 3);
+        bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
+        e.ctr.kernel_launches++;
+    }
+    {
+        PhaseScope ps(e, 4);
+        size_t tb = w.cub_bytes;
+        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, s);
+    }
+    {
+        PhaseScope ps(e, 6);
+        bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
+        e.ctr.kernel_launches++;
+        const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
+        const size_t stride = static_cast<size_t>(n) + 1;
+        scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, len, stride, w.tile_sums, ntiles);
+        scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(w.tile_sums, ntiles);
+        scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, w.p3, len, stride, w.tile_sums, ntiles);
+        e.ctr.kernel_launches += 3;
+    }
+    {
+        PhaseScope ps(e, 5);
+        bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, w.delta, w.close);
+        bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
+        size_t tb = w.cub_bytes;
+        cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
+        BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0, info};
+        bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
+        bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
+        e.ctr.kernel_launches += 4;
+    }
 }
 
 // builds the tree over all e.n bodies and leaves per-local-body acceleration (FAST) / force (EXACT) in w.acc
@@ -871,50 +1042,66 @@ static void bh_forces(Engine& e, float theta) {
         e.ctr.kernel_launches += 2;
     }
     if (e.mode == NBX_MODE_EXACT) {
-        {
+        bool done = false;
+        bool try_parallel = n >= 2;
+        if (const char* ev = getenv("NB_EXACT_PARALLEL")) try_parallel = try_parallel && atoi(ev) != 0;
+        if (try_parallel) {
             PhaseScope ps(e, 5);
-            bh_build_serial_kernel<<<1, 32, 0, s>>>(gp.x, gp.y, gp.m, n, w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
-            bh_finalize_exact_kernel<<<(w.cap_nodes + T - 1) / T, T, 0, s>>>(w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
-            e.ctr.kernel_launches += 2;
+            // (a) is the set merge-free?  bodies sorted by x, each looks ahead through its EPS window
+            NB_CUDA(cudaMemsetAsync(w.xflags, 0, 4 * sizeof(int), s));
+            bh_xkeys_kernel<<<G, T, 0, s>>>(gp.x, n, w.xk, w.idx);
+            size_t tb = w.cub_bytes;
+            cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.xk, w.xk_sorted, w.idx, w.xorder, n, 0, 32, s);
+            bh_close_scan_kernel<<<G, T, 0, s>>>(w.xorder, gp.x, gp.y, n, w.xflags);
+            // (b) the refinement tree, with per-node body ranges
+            build_single_tree(e, w, gp, n, w.info);
+            bh_maxdelta_kernel<<<G, T, 0, s>>>(w.delta, w.dcap, n, w.xflags);
+            e.ctr.kernel_launches += 3;
+            NB_CUDA(cudaMemcpyAsync(w.xflags_host, w.xflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+            NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
+            NB_CUDA(cudaStreamSynchronize(s));
+            if (!w.xflags_host[0] && !w.xflags_host[1] && !w.status_host->overflow) {
+                // (c) exact (px,py,m) of every interior node: fold its bodies in ascending particle index
+                const int maxlev = std::min(w.xflags_host[2], kLevels - 1);
+                for (int l = 0; l <= maxlev; l++) {
+                    const int* idx_l = nullptr;
+                    if (l > 0) {
+                        tb = w.cub_bytes;
+                        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.lk_tmp, w.idx, w.idx_l, n, kKeyBits - 2 * l, kKeyBits, s);
+                        idx_l = w.idx_l;
+                    }
+                    bh_exact_fold_kernel<<<e.num_sms * 4, 128, 0, s>>>(l, w.info, w.status, idx_l, gp.x, gp.y, gp.m, w.nblk);
+                    e.ctr.kernel_launches++;
+                }
+                PhaseScope ps2(e, 0);
+                if (nl > 0) {
+                    bh_traverse_exact_blk_kernel<<<(nl + 127) / 128, 128, 0, s>>>(w.nblk, w.ncblk, gp.x, gp.y, gp.m, ib, nl, theta, w.acc);
+                    e.ctr.kernel_launches++;
+                }
+                TreeTable tt{};
+                tt.blk[0] = w.nblk; tt.cblk[0] = w.ncblk; tt.shift = 31; tt.root = 0u;
+                w.last_tt = tt; w.last_nparts = 1;
+                done = true;
+            }
         }
-        PhaseScope ps(e, 0);
-        if (nl > 0) {
-            bh_traverse_exact_kernel<<<(nl + 127) / 128, 128, 0, s>>>(w.ndata, w.nchild, gp.x, gp.y, gp.m, ib, nl, theta, w.acc);
-            e.ctr.kernel_launches++;
+        if (!done) {
+            {
+                PhaseScope ps(e, 5);
+                bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
+                bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
+                bh_build_serial_kernel<<<1, 32, 0, s>>>(gp.x, gp.y, gp.m, n, w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
+                bh_finalize_exact_kernel<<<(w.cap_nodes + T - 1) / T, T, 0, s>>>(w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
+                e.ctr.kernel_launches += 4;
+            }
+            PhaseScope ps(e, 0);
+            if (nl > 0) {
+                bh_traverse_exact_kernel<<<(nl + 127) / 128, 128, 0, s>>>(w.ndata, w.nchild, gp.x, gp.y, gp.m, ib, nl, theta, w.acc);
+                e.ctr.kernel_launches++;
+            }
+            w.last_nparts = 0;
         }
     } else {
-        {
-            PhaseScope ps(e, 3);
-            bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
-            e.ctr.kernel_launches++;
-        }
-        {
-            PhaseScope ps(e, 4);
-            size_t tb = w.cub_bytes;
-            cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, s);
-        }
-        {
-            PhaseScope ps(e, 6);
-            bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
-            e.ctr.kernel_launches++;
-            const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
-            const size_t stride = static_cast<size_t>(n) + 1;
-            scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, len, stride, w.tile_sums, ntiles);
-            scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(w.tile_sums, ntiles);
-            scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, w.p3, len, stride, w.tile_sums, ntiles);
-            e.ctr.kernel_launches += 3;
-        }
-        {
-            PhaseScope ps(e, 5);
-            bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, w.delta, w.close);
-            bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
-            size_t tb = w.cub_bytes;
-            cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
-            BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0};
-            bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
-            bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
-            e.ctr.kernel_launches += 4;
-        }
+        build_single_tree(e, w, gp, n, nullptr);
         const int* mine = nullptr;
         int n_list = n;
         if (e.dist && e.world > 1) {
@@ -1205,7 +1392,7 @@ static void build_part(Engine& e, BhWork& w, PartBufs& P, const GlobalPos& gp, i
         e.ctr.kernel_launches += 8;
     }
     BuildArgs ba{P.keys_sorted, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, P.nblk, P.ncblk, n, P.cap_blocks - 2,
-                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel};
+                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel, nullptr};
     if (n > 0) {
         const int G = (n + T - 1) / T;
         bh_owner_kernel<<<G, T, 0, s>>>(ba, P.owner, w.status);
@@ -1513,7 +1700,7 @@ void bh_shutdown(Engine& e) {
     BhWork& w = work(e);
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
-    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.cub_tmp); fr(w.status); fr(w.acc);
+    fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.xk); fr(w.xk_sorted); fr(w.xorder); fr(w.idx_l); fr(w.lk_tmp); fr(w.info); fr(w.cub_tmp); fr(w.status); fr(w.acc);
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
     for (auto& g : w.graph) if (g.exec) cudaGraphExecDestroy(g.exec);

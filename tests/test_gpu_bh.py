@@ -67,6 +67,30 @@ def test_exact_c4_size_262144_one_step_bitwise(fresh, oracle):
     assert np.array_equal(bits(g), bits(r))
 
 
+@pytest.mark.parametrize("n,gen", [(20000, "disk"), (65536, "orbits"), (8192, "plummer")])
+def test_exact_parallel_build_is_the_reference_tree_bit_for_bit(fresh, oracle, n, gen, monkeypatch):
+    """EXACT mode on a merge-free set takes the parallel build (sort-based topology + per-node f32 folds in particle
+    index order).  Its tree, dumped in the oracle's format, must equal the reference tree in EVERY bit -- boxes, COMs,
+    masses, flags -- and stepping must agree bitwise with the serial-build path and with the oracle."""
+    s = ic.stable_orbits(n, 0.5, 30.0, seed=6) if gen == "orbits" else \
+        (ic.random_disk(n, seed=6) if gen == "disk" else ic.plummer_2d(n, seed=6))
+    fresh.set_mode(binding.MODE_EXACT)
+    fresh.set_particles(s)
+    fresh.bh_accelerations(0.5)
+    t = fresh.bh_flatten()
+    oracle.set_particles(s)
+    oracle.bh_build()
+    r = oracle.bh_flatten()
+    if t.shape[0] == 0:
+        pytest.skip("this set contains a too-close pair: the serial build ran (covered by the other EXACT tests)")
+    assert t.shape == r.shape and np.array_equal(bits(t), bits(r))
+    g_par = run_gpu(fresh, s, 0.5, 0.01, 3)
+    monkeypatch.setenv("NB_EXACT_PARALLEL", "0")
+    g_ser = run_gpu(fresh, s, 0.5, 0.01, 3)
+    ref = run_ora(oracle, s, 0.5, 0.01, 3, nthreads=4)
+    assert np.array_equal(bits(g_par), bits(ref)) and np.array_equal(bits(g_ser), bits(ref))
+
+
 def test_exact_merge_and_coincident_bodies(fresh, oracle):
     s = ic.random_disk(500, seed=8)
     s[1, :2] = s[0, :2] + f32(3e-5)   # too close: merged leaf (rs-src/nbody.rs:249-260)
