@@ -238,7 +238,7 @@ void x3_step(Engine& e, float dt, int update, float* acc_host) {
     // groups its sums exactly like the 2-D FAST kernel
     const int n_itiles = (s.n + k3TI - 1) / k3TI;
     const int R = e.num_sms * 4;
-    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : 64;
+    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : (n_itiles >= 512 ? 64 : 16);
     int per = (W * R + n_itiles - 1) / n_itiles;
     const int max_per = s.n_pad / k3TJ;
     if (per < 1) per = 1;

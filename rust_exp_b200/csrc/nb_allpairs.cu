@@ -266,7 +266,9 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     const int TI = kComputeThreads * I;
     const int n_itiles = (a.n_local + TI - 1) / TI;
     const int R = e.num_sms * pick_ctas_per_sm(e, I);
-    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : 64;
+    // measured (profiles/r01_sweep_*): many fine slices pay off once there are >= 512 i tiles; below that the
+    // partial-sum traffic and per-item prologue outweigh the better tail
+    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : (n_itiles >= 512 ? 64 : 16);
     int want_total = (W * R + n_itiles - 1) / (n_itiles > 0 ? n_itiles : 1);
     int per_seg = (want_total + a.nseg - 1) / a.nseg;
     const int max_per_seg = L / kTJ;

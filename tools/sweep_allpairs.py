@@ -17,10 +17,12 @@ st = torch.cuda.Stream()
 torch.cuda.set_stream(st)
 lib.set_stream(st.cuda_stream)
 lib.set_particles(ic.plummer_2d(n, seed=3))
-for share in (0, 1, 2):
+shares = (0, 1, 2) if os.environ.get("NB_SWEEP_SHARE") else (0,)
+wave_list = tuple(int(v) for v in os.environ.get("NB_SWEEP_WAVES", "64").split(","))
+for share in shares:
   os.environ["NB_SHARE_RCP"] = str(share)
   for bpt, cps in [(1, 5), (2, 3), (2, 4), (4, 2), (4, 3)]:
-    for waves in (64,):
+    for waves in wave_list:
         lib.tune(bpt, waves, cps)
         for _ in range(2):
             lib.step_brute_force(0.01)
