@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(k3Threads, 3) allpairs3_kernel(const Args3 a) 
             const float4* __restrict__ py = reinterpret_cast<const float4*>(sm.y[s]);
             const float4* __restrict__ pz = reinterpret_cast<const float4*>(sm.z[s]);
             const float4* __restrict__ pm = reinterpret_cast<const float4*>(sm.m[s]);
-#pragma unroll 2
+#pragma unroll 8
             for (int q4 = 0; q4 < k3TJ / 4; q4++) {
                 const float4 X = px[q4], Y = py[q4], Z = pz[q4], M = pm[q4];
 #pragma unroll
@@ -234,18 +234,10 @@ void x3_step(Engine& e, float dt, int update, float* acc_host) {
         NB_CUDA(cudaFuncSetAttribute(allpairs3_kernel<NBX3_LAW_REF>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem3))));
         attr_set = true;
     }
-    // the same decomposition rule as the 2-D kernel (nb_allpairs.cu: allpairs_plan), so that <3,REF> with z = 0
-    // groups its sums exactly like the 2-D FAST kernel
+    // the 2-D kernel's own decomposition rule, so that <3,REF> with z = 0 groups its sums exactly like it
     const int n_itiles = (s.n + k3TI - 1) / k3TI;
-    const int R = e.num_sms * 4;
-    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : (n_itiles >= 512 ? 64 : 16);
-    int per = (W * R + n_itiles - 1) / n_itiles;
-    const int max_per = s.n_pad / k3TJ;
-    if (per < 1) per = 1;
-    if (per > max_per) per = max_per;
-    int slice_len = (s.n_pad + per - 1) / per;
-    slice_len = ((slice_len + k3TJ - 1) / k3TJ) * k3TJ;
-    per = (s.n_pad + slice_len - 1) / slice_len;
+    int slice_len = 0, per = 1;
+    allpairs_slices(e, s.n, s.n_pad, 1, &slice_len, &per);
     const size_t need = static_cast<size_t>(per) * s.n_pad;
     if (need > s.partial_cap) {
         NB_CUDA(cudaStreamSynchronize(e.stream));

@@ -24,6 +24,10 @@ namespace nb {
 
 constexpr int kTJ = 512;             // j bodies per shared-memory tile
 constexpr int kStages = 3;           // TMA ring depth
+#ifndef NB_APQ_UNROLL
+#define NB_APQ_UNROLL 16
+#endif
+constexpr int kQuadUnroll = NB_APQ_UNROLL;   // j quads per unrolled inner-loop body
 constexpr int kDefaultShare = 0;     // reciprocal sharing (see pair4_shared_rcp); measured choice
 constexpr int kComputeWarps = 8;
 constexpr int kComputeThreads = kComputeWarps * 32;
@@ -170,7 +174,7 @@ __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const All
             const float4* __restrict__ px = reinterpret_cast<const float4*>(sm.x[s]);
             const float4* __restrict__ py = reinterpret_cast<const float4*>(sm.y[s]);
             const float4* __restrict__ pm = reinterpret_cast<const float4*>(sm.m[s]);
-#pragma unroll 2
+#pragma unroll kQuadUnroll
             for (int q4 = 0; q4 < kTJ / 4; q4++) {
                 const float4 X = px[q4], Y = py[q4], M = pm[q4];  // broadcast LDS.128
 #pragma unroll
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kExactThreads) allpairs_exact_kernel(const All
 static int pick_bodies_per_thread(const Engine& e) {
     if (e.tune.bodies_per_thread == 1 || e.tune.bodies_per_thread == 2 || e.tune.bodies_per_thread == 4)
         return e.tune.bodies_per_thread;
-    return 2;
+    return 4;   // measured best with 2 CTAs/SM and the 8-quad unroll (profiles/r01_sweep_unroll.txt)
 }
 static int pick_ctas_per_sm(const Engine& e, int I) {
     int c = e.tune.ctas_per_sm > 0 ? e.tune.ctas_per_sm : (I == 1 ? 5 : (I == 2 ? 4 : 2));  // measured best, profiles/
@@ -254,6 +258,28 @@ static int pick_ctas_per_sm(const Engine& e, int I) {
     return c;
 }
 
+// j-slice decomposition of the work (shared with the 3-D extension so that <3,REF> with z = 0 groups its partial
+// sums exactly like this kernel): enough (i tile, j slice) items for `W` waves over the resident CTAs.
+void allpairs_slices(const Engine& e, int n_local, int L, int nseg, int* slice_len_out, int* per_seg_out) {
+    const int I = pick_bodies_per_thread(e);
+    const int TI = kComputeThreads * I;
+    const int n_itiles = (n_local + TI - 1) / TI;
+    const int R = e.num_sms * pick_ctas_per_sm(e, I);
+    // measured (profiles/r01_sweep_*): many fine slices pay off once there are >= 256 i tiles; below that the
+    // partial-sum traffic and per-item prologue outweigh the better tail
+    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : (n_itiles >= 256 ? 64 : 16);
+    int want_total = (W * R + n_itiles - 1) / (n_itiles > 0 ? n_itiles : 1);
+    int per_seg = (want_total + nseg - 1) / nseg;
+    const int max_per_seg = L / kTJ;
+    if (per_seg < 1) per_seg = 1;
+    if (per_seg > max_per_seg) per_seg = max_per_seg;
+    int slice_len = (L + per_seg - 1) / per_seg;
+    slice_len = ((slice_len + kTJ - 1) / kTJ) * kTJ;
+    per_seg = (L + slice_len - 1) / slice_len;
+    *slice_len_out = slice_len;
+    *per_seg_out = per_seg;
+}
+
 void allpairs_plan(Engine& e, AllPairsArgs& a) {
     const int L = static_cast<int>(e.lay.L);
     a.nseg = e.world;
@@ -262,24 +288,8 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     a.i_global_begin = local_begin(e);
     a.n_local = local_count(e);
     a.my_rank = e.rank;
-    const int I = pick_bodies_per_thread(e);
-    const int TI = kComputeThreads * I;
-    const int n_itiles = (a.n_local + TI - 1) / TI;
-    const int R = e.num_sms * pick_ctas_per_sm(e, I);
-    // measured (profiles/r01_sweep_*): many fine slices pay off once there are >= 512 i tiles; below that the
-    // partial-sum traffic and per-item prologue outweigh the better tail
-    const int W = e.tune.target_waves > 0 ? e.tune.target_waves : (n_itiles >= 512 ? 64 : 16);
-    int want_total = (W * R + n_itiles - 1) / (n_itiles > 0 ? n_itiles : 1);
-    int per_seg = (want_total + a.nseg - 1) / a.nseg;
-    const int max_per_seg = L / kTJ;
-    if (per_seg < 1) per_seg = 1;
-    if (per_seg > max_per_seg) per_seg = max_per_seg;
-    int slice_len = (L + per_seg - 1) / per_seg;
-    slice_len = ((slice_len + kTJ - 1) / kTJ) * kTJ;
-    per_seg = (L + slice_len - 1) / slice_len;
-    a.slice_len = slice_len;
-    a.slices_per_seg = per_seg;
-    const size_t need = static_cast<size_t>(a.nseg) * per_seg * L;
+    allpairs_slices(e, a.n_local, L, a.nseg, &a.slice_len, &a.slices_per_seg);
+    const size_t need = static_cast<size_t>(a.nseg) * a.slices_per_seg * L;
     if (need > e.partial_cap) {
         if (e.partial) NB_CUDA(cudaFree(e.partial));
         NB_CUDA(cudaMalloc(&e.partial, need * sizeof(float2)));

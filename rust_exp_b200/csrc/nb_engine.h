@@ -194,6 +194,7 @@ void generate_random_disk(Engine& e, int n);
 void generate_stable_orbits(Engine& e, int n, float rmin, float rmax);
 
 // nb_allpairs.cu
+void allpairs_slices(const Engine& e, int n_local, int L, int nseg, int* slice_len, int* per_seg);
 void allpairs_plan(Engine& e, AllPairsArgs& a);  // fills decomposition fields, grows scratch
 void launch_allpairs_fast(Engine& e, const AllPairsArgs& a);
 void launch_allpairs_exact(Engine& e, const AllPairsArgs& a, float2* force_out);
