@@ -47,7 +47,7 @@ WORKLOADS = {
 DT = 0.01
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
 # `ncu --set full` captures (profiles/r01_ncu_full_*.txt); keyed by (workload, n_gpus)
-TRAFFIC_NCU = {("c3", 1): 28.21e6 + 130.74e6}
+TRAFFIC_NCU = {("c3", 1): 22.55e6 + 111.03e6}
 
 
 def make_ic(w):
