@@ -44,7 +44,8 @@ void nb_random_disk(int32_t num_particles);
 void nb_stable_orbits(int32_t num_particles, float rmin, float rmax);
 
 /* rs-src/nbody.rs:106-162.  One O(N^2) step: forces from OLD positions, then v += (dt*F)/m,
- * p += dt*v.  Asynchronous on the library stream; any nb_get/nb_draw/nbx_synchronize orders after it. */
+ * p += dt*v.  Returns when the GPU has finished the step (the reference's call is synchronous and its host times it
+ * with a wall clock, hs-src/RustNBodyExperiment.hs:55-57); see nbx_set_async for the enqueue-only variant. */
 void nb_step_brute_force(float dt);
 
 /* rs-src/nbody.rs:186-480.  NOTE argument order: theta first.  theta == 0.0 is the brute-force step
@@ -52,7 +53,8 @@ void nb_step_brute_force(float dt);
  * over old positions, per-body tree force with opening test (x2-x1)/d < theta, Euler, then
  * v = 0 for bodies with |px| > 55 or |py| > 55 (rs-src/nbody.rs:466-471).
  * nthreads is the reference's CPU thread-count hint (UI range 1..16): accepted and ignored, except
- * that nthreads <= 0 aborts like the reference's division by zero at rs-src/nbody.rs:426. */
+ * that nthreads <= 0 moves no body, like the reference: its per-thread closure (which holds the division by
+ * nthreads, rs-src/nbody.rs:424-428) is mapped over the empty range 0..nthreads, so the tree is built and dropped. */
 void nb_step_barnes_hut(float theta, float dt, int32_t nthreads);
 
 /* rs-src/nbody.rs:482-583.  Render into the caller-owned w*h ABGR8 framebuffer `fb` (HOST memory, a
@@ -94,6 +96,11 @@ int32_t nbx_get_mode(void);
 int32_t nbx_set_stream(void *cuda_stream);
 int32_t nbx_synchronize(void);
 
+/* Step calls are synchronous by default (they return when the GPU has finished, like the reference's CPU call).
+ * nbx_set_async(1) makes nb_step_* return after enqueueing on the library stream -- any nb_get_particles / nb_draw /
+ * nbx_synchronize still orders after them.  NB_ASYNC_STEPS=1 in the environment selects the same at start-up. */
+int32_t nbx_set_async(int32_t enable);
+
 /* Seed for nb_random_disk / nb_stable_orbits. */
 void nbx_seed(uint64_t seed);
 
@@ -110,10 +117,18 @@ typedef struct nbx_counters {
     uint64_t bh_nodes_visited;
     uint64_t bh_nodes_built;
     uint64_t steps;
+    /* lane efficiency of the warp-cooperative tree walk (counting mode only): stack entries popped by all warps,
+     * and the sum over those pops of the number of lanes (bodies) that needed the entry.  Every pop is evaluated
+     * by all 32 lanes, so bh_pop_lanes / (32 * bh_pops) is the fraction of useful lane work. */
+    uint64_t bh_pops;
+    uint64_t bh_pop_lanes;
 } nbx_counters;
 void nbx_get_counters(nbx_counters *out);
 void nbx_reset_counters(void);
 int32_t nbx_bh_count_interactions(int32_t enable);
+/* Histogram (33 bins, HOST array) of the number of lanes per popped stack entry since the previous call with
+ * reset != 0; filled only while counting is enabled. */
+int32_t nbx_bh_pop_histogram(uint64_t *out33, int32_t reset);
 
 /* Parity aid: the quadtree of the most recent FAST Barnes-Hut call in DFS pre-order (children UL,UR,LL,LR),
  * 9 floats per node {x1,y1,x2,y2, px,py,m, has_children, depth} -- the layout the CPU oracle dumps -- into a HOST
@@ -170,7 +185,15 @@ int32_t nbx_dist_import(const void *all_handles, int32_t world);
 int32_t nbx_dist_nccl_unique_id(void *id_out128);
 int32_t nbx_dist_nccl_init(const void *id128);
 int32_t nbx_dist_set_transport(int32_t transport);
+/* Device-side waits on a peer rank give up (message + trap -> abort) after this long; 0 = wait for ever.
+ * Default 30 s (NB_PEER_TIMEOUT_MS in the environment overrides): long enough for host-side skew between ranks
+ * (initial-condition loading, rank-0-only I/O), short enough that a dead peer does not hang the GPU. */
+int32_t nbx_set_peer_timeout_ms(int32_t ms);
 int32_t nbx_dist_local_range(int32_t *begin, int32_t *count);
+/* Owner-only read-back: fills rows [begin, begin+count) (this rank's shard, see nbx_dist_local_range) of the
+ * caller's FULL n-row AoS array and leaves the other rows untouched -- count*20 bytes of device->host traffic
+ * instead of n*20 on every rank.  Not a collective.  On one GPU it equals nb_get_particles. */
+int32_t nbx_get_particles_local(float *aos5_out_full, int32_t n);
 
 #ifdef __cplusplus
 }

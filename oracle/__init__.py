@@ -42,6 +42,7 @@ class Oracle:
         L.ora_brute_forces_rows.argtypes = [i32, i32, vp]
         L.ora_brute_forces_rows_mt.argtypes = [i32, i32, vp, i32]
         L.ora_step_brute_force.argtypes = [f]
+        L.ora_step_brute_force_mt.argtypes = [f, i32]
         L.ora_step_barnes_hut.argtypes = [f, f, i32]
         L.ora_bh_build.argtypes = []
         L.ora_bh_node_count.restype = i32
@@ -50,6 +51,7 @@ class Oracle:
         L.ora_bh_flatten.restype = i32
         L.ora_bh_forces_rows.argtypes = [f, i32, i32, vp]
         L.ora_bh_count.argtypes = [f, vp, vp]
+        L.ora_bh_count_mt.argtypes = [f, vp, vp, i32]
         L.ora_accel_f64_rows.argtypes = [vp, i32, vp]
         L.ora3_accel_f64.argtypes = [vp, i32, i32, C.c_double, vp, i32, vp]
         L.ora3_step_f64.argtypes = [vp, i32, i32, C.c_double, C.c_double]
@@ -97,8 +99,12 @@ class Oracle:
             self.L.ora_brute_forces_rows_mt(i0, i1, out.ctypes.data, nthreads)
         return out
 
-    def step_brute_force(self, dt: float) -> None:
-        self.L.ora_step_brute_force(dt)
+    def step_brute_force(self, dt: float, nthreads: int = 1) -> None:
+        """nthreads > 1 splits the (independent) force rows over host threads: bit-identical result."""
+        if nthreads <= 1:
+            self.L.ora_step_brute_force(dt)
+        else:
+            self.L.ora_step_brute_force_mt(dt, nthreads)
 
     # -- Barnes-Hut -------------------------------------------------------------------------
     def step_barnes_hut(self, theta: float, dt: float, nthreads: int = 1) -> None:
@@ -125,9 +131,9 @@ class Oracle:
         self.L.ora_bh_forces_rows(theta, i0, i1, out.ctypes.data)
         return out
 
-    def bh_count(self, theta: float) -> tuple[int, int]:
+    def bh_count(self, theta: float, nthreads: int = 0) -> tuple[int, int]:
         a, b = C.c_uint64(0), C.c_uint64(0)
-        self.L.ora_bh_count(theta, C.byref(a), C.byref(b))
+        self.L.ora_bh_count_mt(theta, C.byref(a), C.byref(b), nthreads or (os.cpu_count() or 1))
         return int(a.value), int(b.value)
 
     # -- f64 helper -------------------------------------------------------------------------

@@ -222,6 +222,18 @@ void ora_brute_forces_rows_mt(int32_t i0, int32_t i1, float *fxy_out, int32_t nt
     free(jobs);
 }
 
+/* The same step as ora_step_brute_force with the force rows split over host threads (rows are independent
+ * and every row still accumulates over ascending j, so the result is bit-identical); lets the checker
+ * finish a 65,536-body step in well under a second.  NOT a reference code path. */
+void ora_step_brute_force_mt(float dt, int32_t nthreads)
+{
+    if (g_n == 0) return;
+    float *f = (float *)malloc((size_t)g_n * 2 * sizeof(float));
+    ora_brute_forces_rows_mt(0, g_n, f, nthreads);
+    for (int32_t i = 0; i < g_n; i++) euler(&g_p[i], f[2 * i], f[2 * i + 1], dt);
+    free(f);
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Barnes-Hut.  rs-src/nbody.rs:186-480.
  * ------------------------------------------------------------------------------------------- */
@@ -448,13 +460,44 @@ void ora_bh_forces_rows(float theta, int32_t i0, int32_t i1, float *fxy_out)
     }
 }
 
-void ora_bh_count(float theta, uint64_t *interactions, uint64_t *visited)
+typedef struct { int32_t lo, hi; float theta; uint64_t inter, visited; } CountJob;
+static void *count_worker(void *arg)
 {
+    CountJob *j = (CountJob *)arg;
     uint64_t a = 0, b = 0;
-    for (int32_t i = 0; i < g_n; i++) count_walk(&g_root, g_p[i].px, g_p[i].py, theta, &a, &b);
+    for (int32_t i = j->lo; i < j->hi; i++) count_walk(&g_root, g_p[i].px, g_p[i].py, j->theta, &a, &b);
+    j->inter = a;
+    j->visited = b;
+    return NULL;
+}
+/* bodies are independent and the counts are integers: splitting the loop over threads changes nothing */
+void ora_bh_count_mt(float theta, uint64_t *interactions, uint64_t *visited, int32_t nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    CountJob *jobs = (CountJob *)malloc(sizeof(CountJob) * nthreads);
+    int32_t per = (g_n + nthreads - 1) / nthreads;
+    for (int32_t t = 0; t < nthreads; t++) {
+        jobs[t].lo = t * per < g_n ? t * per : g_n;
+        jobs[t].hi = (t + 1) * per < g_n ? (t + 1) * per : g_n;
+        jobs[t].theta = theta;
+        pthread_create(&th[t], NULL, count_worker, &jobs[t]);
+    }
+    uint64_t a = 0, b = 0;
+    for (int32_t t = 0; t < nthreads; t++) {
+        pthread_join(th[t], NULL);
+        a += jobs[t].inter;
+        b += jobs[t].visited;
+    }
+    free(th);
+    free(jobs);
     *interactions = a;
     *visited = b;
     g_count_interactions = a;
+}
+void ora_bh_count(float theta, uint64_t *interactions, uint64_t *visited)
+{
+    ora_bh_count_mt(theta, interactions, visited, 1);
 }
 
 typedef struct { int32_t lo, hi; float theta, dt; } BhJob;
@@ -483,11 +526,14 @@ void ora_step_barnes_hut(float theta, float dt, int32_t nthreads)
         ora_step_brute_force(dt);
         return;
     }
-    if (nthreads <= 0) { /* rs-src/nbody.rs:426 divides by nthreads: a Rust panic */
-        fprintf(stderr, "oracle: nthreads must be >= 1\n");
-        abort();
-    }
     ora_bh_build();
+    if (nthreads <= 0) {
+        /* rs-src/nbody.rs:424-428: the division by nthreads sits inside the closure mapped over
+         * (0..nthreads); for nthreads <= 0 that range is empty, so the reference builds the tree, spawns
+         * no thread and returns without moving any body. */
+        g_tree_valid = 0;
+        return;
+    }
     /* rs-src/nbody.rs:424-428: range = n / nthreads; last thread takes the remainder */
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
     BhJob *jobs = (BhJob *)malloc(sizeof(BhJob) * nthreads);

@@ -35,11 +35,14 @@ SYMBOLS = {
     "nbx_get_mode": (i32, []),
     "nbx_set_stream": (i32, [vp]),
     "nbx_synchronize": (i32, []),
+    "nbx_set_async": (i32, [i32]),
+    "nbx_set_peer_timeout_ms": (i32, [i32]),
     "nbx_seed": (None, [u64]),
     "nbx_tune": (i32, [i32, i32, i32]),
     "nbx_get_counters": (None, [vp]),
     "nbx_reset_counters": (None, []),
     "nbx_bh_count_interactions": (i32, [i32]),
+    "nbx_bh_pop_histogram": (i32, [vp, i32]),
     "nbx_bh_flatten": (i32, [vp, i32]),
     "nbx_bh_partition": (i32, [i32]),
     "nbx_phase_timing": (i32, [i32]),
@@ -60,6 +63,7 @@ SYMBOLS = {
     "nbx_dist_nccl_init": (i32, [vp]),
     "nbx_dist_set_transport": (i32, [i32]),
     "nbx_dist_local_range": (i32, [vp, vp]),
+    "nbx_get_particles_local": (i32, [vp, i32]),
 }
 
 MODE_FAST, MODE_EXACT = 0, 1
@@ -76,6 +80,8 @@ class Counters(C.Structure):
         ("bh_nodes_visited", u64),
         ("bh_nodes_built", u64),
         ("steps", u64),
+        ("bh_pops", u64),
+        ("bh_pop_lanes", u64),
     ]
 
 
@@ -135,6 +141,13 @@ class NBodyLib:
         self.L.nb_get_particles(out.ctypes.data, n)
         return out
 
+    def get_particles_local(self, out: np.ndarray) -> np.ndarray:
+        """Owner-only read-back into the caller's full (n,5) array: only this rank's rows are written."""
+        n = self.num_particles()
+        assert out.dtype == np.float32 and out.size >= 5 * n and out.flags.c_contiguous
+        self._chk(self.L.nbx_get_particles_local(out.ctypes.data, n), "nbx_get_particles_local")
+        return out
+
     # ---- extensions ------------------------------------------------------------------------------
     def _chk(self, rc: int, what: str) -> None:
         if rc != 0:
@@ -164,6 +177,12 @@ class NBodyLib:
     def synchronize(self) -> None:
         self._chk(self.L.nbx_synchronize(), "nbx_synchronize")
 
+    def set_async(self, on: bool) -> None:
+        self._chk(self.L.nbx_set_async(1 if on else 0), "nbx_set_async")
+
+    def set_peer_timeout_ms(self, ms: int) -> None:
+        self._chk(self.L.nbx_set_peer_timeout_ms(ms), "nbx_set_peer_timeout_ms")
+
     def seed(self, s: int) -> None:
         self.L.nbx_seed(s)
 
@@ -180,6 +199,11 @@ class NBodyLib:
 
     def bh_count_interactions(self, on: bool) -> None:
         self.L.nbx_bh_count_interactions(1 if on else 0)
+
+    def bh_pop_histogram(self, reset: bool = True) -> np.ndarray:
+        out = np.zeros(33, dtype=np.uint64)
+        self._chk(self.L.nbx_bh_pop_histogram(out.ctypes.data, 1 if reset else 0), "nbx_bh_pop_histogram")
+        return out
 
     def bh_flatten(self) -> np.ndarray:
         n = int(self.L.nbx_bh_flatten(None, 0))

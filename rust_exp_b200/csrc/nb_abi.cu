@@ -54,11 +54,14 @@ void nb_stable_orbits(int32_t num_particles, float rmin, float rmax) {
     replace_set_end(e);
 }
 
-// NB_SYNC_STEPS=1 makes every step call return only when the GPU has finished it, like the reference's
-// synchronous CPU call -- for hosts that put a wall-clock timer around the step (hs-src/RustNBodyExperiment.hs:55-57).
+// Step calls return only when the GPU has finished the step, like the reference's synchronous CPU call: its host
+// puts a wall-clock timer around the step (hs-src/RustNBodyExperiment.hs:55-57, timeIt) and would otherwise display
+// launch latency.  nbx_set_async(1) (or NB_ASYNC_STEPS=1 in the environment) makes steps return after enqueueing;
+// nb_get_particles / nb_draw / nbx_synchronize still order after them.
+static int g_async = -1;
 static bool sync_steps() {
-    static const bool v = [] { const char* s = getenv("NB_SYNC_STEPS"); return s && atoi(s) != 0; }();
-    return v;
+    if (g_async < 0) { const char* s = getenv("NB_ASYNC_STEPS"); g_async = (s && atoi(s) != 0) ? 1 : 0; }
+    return g_async == 0;
 }
 
 // rs-src/nbody.rs:106-162
@@ -78,7 +81,9 @@ void nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
     if (theta == 0.0f) {  // rs-src/nbody.rs:197-200 (before nthreads is ever used)
         step_brute_force(e, dt);
     } else {
-        if (nthreads <= 0) fatal("nb_step_barnes_hut: nthreads must be >= 1 (the reference divides by it)", __FILE__, __LINE__);
+        // rs-src/nbody.rs:424-428: the division by nthreads sits inside the closure mapped over (0..nthreads); for
+        // nthreads <= 0 that range is empty -- the reference builds the tree and returns without moving any body.
+        if (nthreads <= 0) return;
         bh_step(e, theta, dt);
     }
     if (sync_steps()) NB_CUDA(cudaStreamSynchronize(e.stream));
@@ -114,6 +119,15 @@ void nb_get_particles(float* aos5_out, int32_t n) {
 }
 
 // ---- extension surface ----------------------------------------------------------------------------
+int32_t nbx_get_particles_local(float* aos5_out_full, int32_t n) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    state_download_local(e, aos5_out_full, n);
+    if (e.bh) bh_poll(e);
+    return 0;
+}
+
 int32_t nbx_init(int32_t device) {
     NB_LOCK();
     return try_init(engine(), device);
@@ -137,12 +151,15 @@ void nbx_shutdown(void) {
     if (e.force) cudaFree(e.force);
     if (e.stage_dev) cudaFree(e.stage_dev);
     for (int p = 0; p < NBX_NUM_PHASES; p++)
-        for (int k = 0; k < Engine::kPhaseRing; k++)
-            for (int j = 0; j < 2; j++)
-                if (e.ev[p][k][j]) {
-                    cudaEventDestroy(e.ev[p][k][j]);
-                    e.ev[p][k][j] = nullptr;
-                }
+        for (int k = 0; k < Engine::kPhaseRing; k++) {
+            e.ev_sub[p][k] = 0;
+            for (int u = 0; u < Engine::kPhaseSub; u++)
+                for (int j = 0; j < 2; j++)
+                    if (e.ev[p][k][u][j]) {
+                        cudaEventDestroy(e.ev[p][k][u][j]);
+                        e.ev[p][k][u][j] = nullptr;
+                    }
+        }
     if (e.own_stream) cudaStreamDestroy(e.own_stream);
     (void)cudaGetLastError();
     // reset to a fresh engine (keep the mutex)
@@ -150,12 +167,23 @@ void nbx_shutdown(void) {
     e.arena.base = nullptr; e.mirror = nullptr; e.partial = nullptr; e.force = nullptr;
     e.stage_dev = nullptr; e.own_stream = nullptr; e.stream = nullptr;
     e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = 0;
-    e.lay = ArenaLayout(); e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
+    e.lay = ArenaLayout(); e.L_cap = 0; e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
     e.cur = 0; e.step_count = 0; e.mode = NBX_MODE_FAST; e.tune = Tuning(); e.ctr = nbx_counters{};
     e.transport = NBX_TRANSPORT_P2P_DIRECT; e.max_particles = 0; e.mirror_mass_valid = false; e.bh_partition = 0;
     e.bh_count = false; e.phase_timing = false; e.ev_slot = 0; e.bh_lay = BhArenaLayout();
     for (int p = 0; p < NBX_NUM_PHASES; p++) e.ev_count[p] = 0;
     for (int g = 0; g < kMaxRanks; g++) { e.peer[g].base = nullptr; e.bh_peer[g] = nullptr; }
+}
+
+int32_t nbx_set_async(int32_t enable) {
+    NB_LOCK();
+    g_async = enable != 0 ? 1 : 0;
+    return 0;
+}
+int32_t nbx_set_peer_timeout_ms(int32_t ms) {
+    NB_LOCK();
+    engine().peer_timeout_ns = ms <= 0 ? 0ull : static_cast<uint64_t>(ms) * 1000000ull;
+    return 0;
 }
 
 const char* nbx_last_error(void) { return last_error(); }
@@ -232,6 +260,14 @@ int32_t nbx_bh_count_interactions(int32_t enable) {
     return 0;
 }
 
+int32_t nbx_bh_pop_histogram(uint64_t* out33, int32_t reset) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    bh_pop_histogram(e, out33, reset != 0);
+    return 0;
+}
+
 int32_t nbx_bh_flatten(float* out9, int32_t cap) {
     NB_LOCK();
     Engine& e = engine();
@@ -254,7 +290,10 @@ int32_t nbx_phase_timing(int32_t enable) {
     Engine& e = engine();
     e.phase_timing = enable != 0;
     e.ev_slot = 0;
-    for (int p = 0; p < NBX_NUM_PHASES; p++) e.ev_count[p] = 0;
+    for (int p = 0; p < NBX_NUM_PHASES; p++) {
+        e.ev_count[p] = 0;
+        for (int k = 0; k < Engine::kPhaseRing; k++) e.ev_sub[p][k] = 0;
+    }
     return 0;
 }
 int32_t nbx_get_phase_ms(float* out8) {

@@ -76,21 +76,6 @@ __device__ __forceinline__ void pair4_shared_rcp(const float4 X, const float4 Y,
     ax = __ffma2_rn(sb, dxb, ax); ay = __ffma2_rn(sb, dyb, ay);
 }
 
-// Spin until rank g has published step >= want (P2P_DIRECT ordering).  Bounded: a dead peer must not
-// hang the GPU (a hung box is a lost box) -- after ~4 s we trap.
-__device__ __forceinline__ void wait_flag(const uint32_t* flags, int g, uint32_t want) {
-    const volatile uint32_t* f = flags + g;
-    long long t0 = clock64();
-    while (static_cast<int32_t>(*f - want) < 0) {
-        __nanosleep(200);
-        if (clock64() - t0 > 8000000000LL) {
-            printf("nbody_b200: timeout waiting for rank %d to reach step %u (at %u)\n", g, want, *f);
-            __trap();
-        }
-    }
-    __threadfence_system();
-}
-
 template <int I, int MINB, int SHARE>
 __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const AllPairsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -125,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const All
                 const int sl = gslice - q * a.slices_per_seg;
                 const int g = (a.my_rank + q) % a.nseg;
                 if (a.flags != nullptr && !(seen_mask & (1u << g))) {
-                    wait_flag(a.flags, g, a.wait_step);
+                    wait_epoch(a.flags + g, a.wait_step, a.timeout_ns, g, "step");
                     seen_mask |= 1u << g;
                 }
                 const int j0 = sl * a.slice_len;
@@ -288,6 +273,7 @@ void allpairs_plan(Engine& e, AllPairsArgs& a) {
     a.i_global_begin = local_begin(e);
     a.n_local = local_count(e);
     a.my_rank = e.rank;
+    a.timeout_ns = e.peer_timeout_ns;
     allpairs_slices(e, a.n_local, L, a.nseg, &a.slice_len, &a.slices_per_seg);
     const size_t need = static_cast<size_t>(a.nseg) * a.slices_per_seg * L;
     if (need > e.partial_cap) {

@@ -56,6 +56,11 @@ struct BhStatus {
     int n_top;                // partitioned build: interior nodes of the shared top tree
     unsigned long long interactions;
     unsigned long long visited;
+    // walk scheduling + lane-efficiency instrumentation (COUNT builds of the walk only)
+    int tickets[kMaxRanks + 1];           // next group of 32 bodies per walk launch (dynamic scheduling)
+    unsigned long long pops;              // stack entries popped by all warps
+    unsigned long long pop_lanes;         // sum of popcount(lane mask) over those pops
+    unsigned long long pop_hist[33];      // histogram of popcount(lane mask)
 };
 
 constexpr int kCutLevel = 5;
@@ -155,8 +160,10 @@ struct BhWork {
         cudaStream_t stream = nullptr;
         uint64_t launches = 0;
         const char* arena = nullptr;
+        uint64_t alloc_gen = 0;
+        size_t L = 0;
     } graph[2];
-    int graph_misses = 0;
+    uint64_t alloc_gen = 0;          // bumped whenever a buffer a captured graph points at is (re)allocated
     bool capturing = false;
     // domain-partitioned mode
     std::vector<PartBufs> parts;
@@ -166,6 +173,7 @@ struct BhWork {
     TreeTable last_tt{};             // the tree of the most recent FAST step (for nbx_bh_flatten)
     int last_nparts = 0;             // 0 = no FAST tree yet, 1 = single tree, >1 = partitioned
     bool last_partitioned = false;
+    uint64_t pop_hist[33] = {};      // lane-mask popcount histogram of the walk (counting mode), since the last read
 };
 
 static BhWork& work(Engine& e) {
@@ -193,6 +201,10 @@ __global__ void bh_reset_kernel(BhStatus* st) {
         st->visited = 0;
         st->n_deep = 0;
         st->n_top = 0;
+        for (int g = 0; g <= kMaxRanks; g++) st->tickets[g] = 0;
+        st->pops = 0;
+        st->pop_lanes = 0;
+        for (int k = 0; k < 33; k++) st->pop_hist[k] = 0;
     }
 }
 
@@ -404,6 +416,7 @@ struct BuildArgs {
     unsigned part_off;   // added to every child block index (global block index space of partitioned trees)
     int cut_level;       // partitioned build: interior nodes at levels >= cut_level are counted in n_deep
     struct NodeInfo* info;   // EXACT parallel build: per interior node its body range, level and own record slot
+    int store_sq;            // FAST: the 4th record field is s*s (the walk's opening test compares squares); EXACT: s
 };
 
 __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
@@ -492,7 +505,8 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
             a.nblk[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M), 0.f, 0.f, 0.f);
             a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
             a.nblk[2] = make_float4(static_cast<float>(M), 0.f, 0.f, 0.f);
-            a.nblk[3] = make_float4(__fsub_rn(x2, x1), -1.f, -1.f, -1.f);
+            const float s0 = __fsub_rn(x2, x1);
+            a.nblk[3] = make_float4(a.store_sq ? __fmul_rn(s0, s0) : s0, -1.f, -1.f, -1.f);
             a.ncblk[0] = make_int4(static_cast<int>(a.part_off) + blk, -1, -1, -1);
         }
         float4 rec[4];
@@ -516,7 +530,8 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                     const double MY = a.p3[2 * stride + first + cnt] - a.p3[2 * stride + first];
                     // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
-                    rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M), s);
+                    rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M),
+                                         a.store_sq ? __fmul_rn(s, s) : s);
                     chp[q] = static_cast<int>(a.part_off) + 1 + cid;
                     if (a.info) { a.info[cid].blk = blk; a.info[cid].slot_level = q | ((l + 1) << 8); }
                 } else {
@@ -604,94 +619,117 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 }
 
 // ---- traversal, FAST ---------------------------------------------------------------------------------------
-// One warp per 32 Morton-consecutive bodies.  Stack entries are (node block, mask of lanes that must look at
-// it).  A block is the four children of an opened node in SoA form (x[4] y[4] m[4] s[4], 64 bytes): the warp
-// evaluates all four branch-free with packed FP32 -- a lane in the mask interacts with a child if it is a
-// leaf or passes the reference's per-body opening test (rs-src/nbody.rs:345), otherwise it asks for the
-// child to be opened; only children that some lane must open are pushed, with that lane mask.  Every body
-// therefore evaluates exactly the reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and
-// the body's own leaf (d = 0, :365) need no test: their contribution is an exact zero because EPS > 0.
-template <bool COUNT>
+// One warp per 32 Morton-consecutive bodies; warps fetch groups from a ticket counter (persistent grid, no tail).
+// Stack entries are (node block, mask of lanes that must look at it).  A block is the four children of an opened
+// node in SoA form (x[4] y[4] m[4] q[4], 64 bytes; q = s*s of the child's cell for an interior child, -1 for a
+// leaf or an empty slot): the warp evaluates all four branch-free with packed FP32.  A lane in the mask interacts
+// with a child if it passes the reference's per-body opening test s/d < theta (rs-src/nbody.rs:345, as
+// s^2 < theta^2 d^2) -- which a leaf's q = -1 always passes -- otherwise it asks for the child to be opened; only
+// children that some lane must open are pushed, with that lane mask.  Every body therefore evaluates exactly the
+// reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and the body's own leaf (d = 0, :365) need
+// no test: their contribution is an exact zero because EPS > 0.
+// Lanes outside an entry's mask run with theta^2 = NaN: both `q < t` and the derived open mask are then false
+// without any per-child predicate logic.
+template <bool COUNT, bool PARTS>
 __global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
-    float theta2, BhStatus* st) {
+    float theta2, BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
+    unsigned* __restrict__ cell_work) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * kTravWarps + warp;
-    const int li = w * 32 + lane;
-    if (w * 32 >= n_list) return;
-    const bool live = li < n_list;
-    const int pos = live ? (mine ? mine[li] : li) : 0;  // position in sorted order
-    const float px = sx[pos], py = sy[pos];
-    const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
-    const float2 eps2 = make_float2(kEps, kEps), th2 = make_float2(theta2, theta2);
-    float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+    const unsigned lanebit = 1u << lane;
+    const int ngroups = (n_list + 31) >> 5;
+    const float qnan = __int_as_float(0x7fffffff);
+    const float2 eps2 = make_float2(kEps, kEps);
     uint2* s = stk[warp];
-    int sp = 0;
-    unsigned long long n_int = 0, n_vis = 0;
-    {
-        const unsigned m0 = __ballot_sync(0xffffffffu, live);
-        if (lane == 0) s[0] = make_uint2(tt.root, m0);   // root block = {root, empty, empty, empty}
-        sp = 1;
-        __syncwarp();
-        if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
-    }
-    while (sp > 0) {
-        --sp;
-        const uint2 e = s[sp];
-        __syncwarp();
-        const bool act = (e.y >> lane) & 1u;
-        const unsigned part = e.x >> tt.shift, bi = e.x & ((1u << tt.shift) - 1u);
-        const float4* __restrict__ nb4 = tt.blk[part] + 4 * static_cast<size_t>(bi);
-        const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), S = __ldg(nb4 + 3);
-        const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
-        const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
-        const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
-        const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
-        const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
-        // opening test s/d < theta  <=>  s^2 < theta^2 d^2   (s < 0 marks a leaf)
-        const float2 t01 = __fmul2_rn(th2, d01), t23 = __fmul2_rn(th2, d23);
-        const float2 q01 = __fmul2_rn(make_float2(S.x, S.y), make_float2(S.x, S.y));
-        const float2 q23 = __fmul2_rn(make_float2(S.z, S.w), make_float2(S.z, S.w));
-        const bool l0 = S.x < 0.f, l1 = S.y < 0.f, l2 = S.z < 0.f, l3 = S.w < 0.f;
-        const bool a0 = q01.x < t01.x, a1 = q01.y < t01.y, a2 = q23.x < t23.x, a3 = q23.y < t23.y;
-        const bool u0 = act && (l0 || a0), u1 = act && (l1 || a1), u2 = act && (l2 || a2), u3 = act && (l3 || a3);
-        float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
-        float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
-        c01.x = u0 ? c01.x : 0.f; c01.y = u1 ? c01.y : 0.f;
-        c23.x = u2 ? c23.x : 0.f; c23.y = u3 ? c23.y : 0.f;
-        ax = __ffma2_rn(c01, dx01, ax); ay = __ffma2_rn(c01, dy01, ay);
-        ax = __ffma2_rn(c23, dx23, ax); ay = __ffma2_rn(c23, dy23, ay);
-        const unsigned ob = (act && !l0 && !a0 ? 1u : 0u) | (act && !l1 && !a1 ? 2u : 0u) |
-                            (act && !l2 && !a2 ? 4u : 0u) | (act && !l3 && !a3 ? 8u : 0u);
-        if (COUNT) {
-            n_vis += act ? 4 : 0;
-            n_int += (u0 && M.x != 0.f && !(X.x == px && Y.x == py)) + (u1 && M.y != 0.f && !(X.y == px && Y.y == py)) +
-                     (u2 && M.z != 0.f && !(X.z == px && Y.z == py)) + (u3 && M.w != 0.f && !(X.w == px && Y.w == py));
+    unsigned long long n_int = 0, n_vis = 0, n_pop = 0, n_lane = 0;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(&st->tickets[ticket_slot], 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= ngroups) break;
+        const int li = w * 32 + lane;
+        const bool live = li < n_list;
+        const int pos = live ? (mine ? mine[li] : li) : 0;  // position in sorted order
+        const float px = sx[pos], py = sy[pos];
+        const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
+        float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
+        int sp = 1;
+        unsigned my_pops = 0;
+        {
+            const unsigned m0 = __ballot_sync(0xffffffffu, live);
+            if (lane == 0) s[0] = make_uint2(tt.root, m0);   // root block = {root, empty, empty, empty}
+            __syncwarp();
+            if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
         }
-        const unsigned any = __reduce_or_sync(0xffffffffu, ob);
-        if (any) {
-            const int4 C = __ldg(tt.cblk[part] + bi);
-            // push order 3..0 so that child 0 is opened first (DFS-like order)
-            if (any & 8u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 8u); if (lane == 0) s[sp] = make_uint2(C.w, om); sp++; }
-            if (any & 4u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 4u); if (lane == 0) s[sp] = make_uint2(C.z, om); sp++; }
-            if (any & 2u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 2u); if (lane == 0) s[sp] = make_uint2(C.y, om); sp++; }
-            if (any & 1u) { const unsigned om = __ballot_sync(0xffffffffu, ob & 1u); if (lane == 0) s[sp] = make_uint2(C.x, om); sp++; }
+        while (sp > 0) {
+            --sp;
+            const uint2 e = s[sp];
+            __syncwarp();
+            const bool act = (e.y & lanebit) != 0u;
+            const float thx = act ? theta2 : qnan;
+            const float4* __restrict__ nb4;
+            unsigned part = 0, bi = e.x;
+            if (PARTS) {
+                part = e.x >> kPartShift; bi = e.x & ((1u << kPartShift) - 1u);
+                nb4 = tt.blk[part] + 4 * static_cast<size_t>(bi);
+            } else {
+                nb4 = tt.blk[0] + 4 * static_cast<size_t>(bi);
+            }
+            const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), Q = __ldg(nb4 + 3);
+            const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
+            const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
+            const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
+            const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
+            const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
+            // opening test s/d < theta  <=>  s^2 < theta^2 d^2 ; false for every child when the lane is not in the mask
+            const float2 t01 = __fmul2_rn(d01, make_float2(thx, thx)), t23 = __fmul2_rn(d23, make_float2(thx, thx));
+            const bool a0 = Q.x < t01.x, a1 = Q.y < t01.y, a2 = Q.z < t23.x, a3 = Q.w < t23.y;
+            float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
+            float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
+            c01.x = a0 ? c01.x : 0.f; c01.y = a1 ? c01.y : 0.f;
+            c23.x = a2 ? c23.x : 0.f; c23.y = a3 ? c23.y : 0.f;
+            ax = __ffma2_rn(c01, dx01, ax); ay = __ffma2_rn(c01, dy01, ay);
+            ax = __ffma2_rn(c23, dx23, ax); ay = __ffma2_rn(c23, dy23, ay);
+            // lanes of the mask that did not accept child k must open it
+            const unsigned o0 = e.y & ~__ballot_sync(0xffffffffu, a0), o1 = e.y & ~__ballot_sync(0xffffffffu, a1);
+            const unsigned o2 = e.y & ~__ballot_sync(0xffffffffu, a2), o3 = e.y & ~__ballot_sync(0xffffffffu, a3);
+            if (COUNT) {
+                n_vis += act ? 4 : 0;
+                n_int += (a0 && M.x != 0.f && !(X.x == px && Y.x == py)) + (a1 && M.y != 0.f && !(X.y == px && Y.y == py)) +
+                         (a2 && M.z != 0.f && !(X.z == px && Y.z == py)) + (a3 && M.w != 0.f && !(X.w == px && Y.w == py));
+                if (lane == 0) { n_pop++; n_lane += __popc(e.y); atomicAdd(&st->pop_hist[__popc(e.y)], 1ull); }
+            }
+            my_pops++;
+            if (o0 | o1 | o2 | o3) {
+                const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
+                // push order 3..0 so that child 0 is opened first (DFS-like order).  Branch-free: every lane stores the
+                // same (warp-uniform) entry to the same slot, and the slot only counts if its lane mask is non-empty.
+                s[sp] = make_uint2(C.w, o3); sp += (o3 != 0u);
+                s[sp] = make_uint2(C.z, o2); sp += (o2 != 0u);
+                s[sp] = make_uint2(C.y, o1); sp += (o1 != 0u);
+                s[sp] = make_uint2(C.x, o0); sp += (o0 != 0u);
+            }
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    if (live) {
-        const int gi = idx_sorted[pos];
-        const int own = gi / tt.shard_len;
-        tt.acc[own][gi - own * tt.shard_len] = make_float2(ax.x + ax.y, ay.x + ay.y);
+        if (live) {
+            const int gi = idx_sorted[pos];
+            const int own = gi / tt.shard_len;
+            tt.acc[own][gi - own * tt.shard_len] = make_float2(ax.x + ax.y, ay.x + ay.y);
+        }
+        if (cell_work != nullptr && lane == 0)   // partition weights for the next step: walk cost per cut-level cell
+            atomicAdd(&cell_work[static_cast<unsigned>(keys_sorted[pos] >> kCellShift)], my_pops);
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) {
             n_int += __shfl_xor_sync(0xffffffffu, n_int, o);
             n_vis += __shfl_xor_sync(0xffffffffu, n_vis, o);
         }
-        if (lane == 0) { atomicAdd(&st->interactions, n_int); atomicAdd(&st->visited, n_vis); }
+        if (lane == 0) {
+            atomicAdd(&st->interactions, n_int); atomicAdd(&st->visited, n_vis);
+            atomicAdd(&st->pops, n_pop); atomicAdd(&st->pop_lanes, n_lane);
+        }
     }
 }
 
@@ -903,13 +941,27 @@ static int bh_partition_count(const Engine& e) {
     return parts > 1 ? parts : 1;
 }
 
+static int traverse_resident_blocks(Engine& e) {
+    static int per_sm = 0;
+    if (!per_sm) {
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false>, kTravWarps * 32, 0));
+        if (per_sm < 1) per_sm = 1;
+    }
+    return per_sm * e.num_sms;
+}
+
+// ticket_slot: which st->tickets[] counter this launch draws its groups from (one per launch between two resets)
 static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, const float* sy, const int* idx_sorted,
-                            const int* mine, int n_list, float theta, BhStatus* st) {
-    const int blocks = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
-    if (e.bh_count)
-        bh_traverse_fast_kernel<true><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, theta * theta, st);
-    else
-        bh_traverse_fast_kernel<false><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, theta * theta, st);
+                            const int* mine, int n_list, float theta, BhStatus* st, int ticket_slot = 0,
+                            const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr) {
+    const int want = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
+    const int blocks = std::min(want, traverse_resident_blocks(e));
+    const bool parts = tt.shift != 31;
+    const float th2 = theta * theta;
+#define NB_TRAV(C, P) bh_traverse_fast_kernel<C, P><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work)
+    if (e.bh_count) { if (parts) NB_TRAV(true, true); else NB_TRAV(true, false); }
+    else { if (parts) NB_TRAV(false, true); else NB_TRAV(false, false); }
+#undef NB_TRAV
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
 }
@@ -946,6 +998,7 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
         w.cub_bytes = std::max(b1, std::max(b2, b3)) + 256;
         NB_CUDA(cudaMalloc(&w.cub_tmp, w.cub_bytes));
         w.cap_n = n;
+        w.alloc_gen++;
     }
 }
 
@@ -1001,7 +1054,8 @@ static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, 
         bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
         size_t tb = w.cub_bytes;
         cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
-        BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0, info};
+        BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0, info,
+                     info ? 0 : 1};
         bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
         bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
         e.ctr.kernel_launches += 4;
@@ -1017,9 +1071,11 @@ static void bh_forces(Engine& e, float theta) {
     ensure_work(e, w, n);
     const int nl = local_count(e), ib = local_begin(e);
     if (nl > w.cap_acc) {
+        NB_CUDA(cudaStreamSynchronize(e.stream));
         if (w.acc) NB_CUDA(cudaFree(w.acc));
         NB_CUDA(cudaMalloc(&w.acc, sizeof(float2) * static_cast<size_t>(e.lay.L)));
         w.cap_acc = static_cast<int>(e.lay.L);
+        w.alloc_gen++;
     }
     w.acc_src = w.acc;
     w.last_partitioned = false;
@@ -1245,6 +1301,7 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
     __syncthreads();
     __shared__ int s_top;
     if (tid == 0) s_top = 0;
+    __syncthreads();
     for (int l = kCutLevel - 1; l >= 0; l--) {
         const int off = top_off_level(l), offc = top_off_level(l + 1);
         for (int p = tid; p < (1 << (2 * l)); p += blockDim.x) {
@@ -1276,8 +1333,9 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
         else ch = static_cast<int>(a.top_off) + 1 + node;   // top block of an interior top node
         if (ch < 0) { rec = make_float4(lf.x, lf.y, lf.z, -1.0f); return; }   // merged cell at the cut level
         const double M = a.tm3[node];
+        const float cw = cell_width(st, level, path);
         rec = make_float4(static_cast<float>(a.tm3[kTopNodes + node] / M), static_cast<float>(a.tm3[2 * kTopNodes + node] / M),
-                          static_cast<float>(M), cell_width(st, level, path));
+                          static_cast<float>(M), __fmul_rn(cw, cw));
         child = ch;
     };
     // block 0: {root, empty, empty, empty}; block 1 + node: the four children of interior top node `node`
@@ -1313,20 +1371,9 @@ __global__ void bh_flag_signal_kernel(PeerU32 peers, int world, int slot, uint32
         __threadfence_system();
     }
 }
-__global__ void bh_flag_wait_kernel(const uint32_t* flags, int world, uint32_t want) {
+__global__ void bh_flag_wait_kernel(const uint32_t* flags, int world, uint32_t want, unsigned long long timeout_ns) {
     const int g = threadIdx.x;
-    if (g < world) {
-        const volatile uint32_t* f = flags + g;
-        const long long t0 = clock64();
-        while (static_cast<int32_t>(*f - want) < 0) {
-            __nanosleep(200);
-            if (clock64() - t0 > 8000000000LL) {   // ~4 s: a dead peer must not hang this GPU
-                printf("nbody_b200: timeout waiting for rank %d (Barnes-Hut epoch %u, at %u)\n", g, want, *f);
-                __trap();
-            }
-        }
-        __threadfence_system();
-    }
+    if (g < world) wait_epoch(flags + g, want, timeout_ns, g, "Barnes-Hut epoch");
 }
 
 static void part_ensure(Engine& e, BhWork& w, PartBufs& P, int n, bool in_arena) {
@@ -1392,7 +1439,7 @@ static void build_part(Engine& e, BhWork& w, PartBufs& P, const GlobalPos& gp, i
         e.ctr.kernel_launches += 8;
     }
     BuildArgs ba{P.keys_sorted, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, P.nblk, P.ncblk, n, P.cap_blocks - 2,
-                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel, nullptr};
+                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel, nullptr, 1};
     if (n > 0) {
         const int G = (n + T - 1) / T;
         bh_owner_kernel<<<G, T, 0, s>>>(ba, P.owner, w.status);
@@ -1479,7 +1526,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PeerU32 pf{};
         for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags);
         bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
-        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags), e.world, epoch);
+        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags), e.world, epoch, e.peer_timeout_ns);
         e.ctr.kernel_launches += 2;
         for (int g = 0; g < e.world; g++) {
             ta.tab[g] = reinterpret_cast<const CellEntry*>(e.bh_peer[g] + e.bh_lay.off_celltab);
@@ -1510,7 +1557,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nparts; r++) {
             if (real && r != e.rank) continue;
             PartBufs& P = w.parts[real ? 0 : r];
-            if (P.n > 0) launch_traverse(e, tt, P.sx, P.sy, P.idx_sorted, nullptr, P.n, theta, w.status);
+            if (P.n > 0) launch_traverse(e, tt, P.sx, P.sy, P.idx_sorted, nullptr, P.n, theta, w.status, real ? 0 : r);
         }
     }
     if (real) {
@@ -1520,7 +1567,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PeerU32 pf{};
         for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags) + kMaxRanks;
         bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
-        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags) + kMaxRanks, e.world, epoch);
+        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags) + kMaxRanks, e.world, epoch, e.peer_timeout_ns);
         e.ctr.kernel_launches += 2;
         w.acc_src = reinterpret_cast<float2*>(e.bh_arena + e.bh_lay.off_acc);
     } else {
@@ -1551,6 +1598,16 @@ static void check_status(Engine& e, BhWork& w, bool sync_now) {
         e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
     e.ctr.bh_interactions += h.interactions;
     e.ctr.bh_nodes_visited += h.visited;
+    e.ctr.bh_pops += h.pops;
+    e.ctr.bh_pop_lanes += h.pop_lanes;
+    for (int k = 0; k < 33; k++) w.pop_hist[k] += h.pop_hist[k];
+}
+void bh_pop_histogram(Engine& e, uint64_t* out33, bool reset) {
+    for (int k = 0; k < 33; k++) out33[k] = 0;
+    if (!e.bh) return;
+    BhWork& w = work(e);
+    check_status(e, w, true);
+    for (int k = 0; k < 33; k++) { out33[k] = w.pop_hist[k]; if (reset) w.pop_hist[k] = 0; }
 }
 void bh_poll(Engine& e) {
     if (e.bh) check_status(e, work(e), true);
@@ -1575,20 +1632,26 @@ static bool bh_graph_eligible(const Engine& e) {
 void bh_step(Engine& e, float theta, float dt) {
     if (e.n == 0) return;
     BhWork& w = work(e);
-    if (bh_graph_eligible(e) && w.graph_misses < 16) {
+    if (bh_graph_eligible(e)) {
         ensure_status(w);
         check_status(e, w, false);
         ensure_work(e, w, e.n);
         if (local_count(e) > w.cap_acc) {   // same sizing rule as bh_forces: allocate outside the capture
+            NB_CUDA(cudaStreamSynchronize(e.stream));
             if (w.acc) NB_CUDA(cudaFree(w.acc));
             NB_CUDA(cudaMalloc(&w.acc, sizeof(float2) * static_cast<size_t>(e.lay.L)));
             w.cap_acc = static_cast<int>(e.lay.L);
+            w.alloc_gen++;
         }
         BhWork::GraphSlot& g = w.graph[e.cur];
+        // every pointer and scalar a captured launch carries is a function of this key (alloc_gen covers the workspace)
         const bool hit = g.exec && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
-                         g.arena == e.arena.base;
+                         g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L;
         if (!hit) {
-            if (g.exec) { NB_CUDA(cudaGraphExecDestroy(g.exec)); g.exec = nullptr; w.graph_misses++; }
+            // Re-capture (host-only work, ~20 nodes) and patch the instantiated graph in place: a theta / dt change
+            // from the reference UI (hs-src/RustNBodyExperiment.hs:88-93) or a reallocation only changes kernel
+            // parameters, not the topology, so cudaGraphExecUpdate succeeds; a different n changes grid sizes, which
+            // it also accepts.  Only if the update is refused is the graph re-instantiated.
             const int cur0 = e.cur;
             const uint64_t l0 = e.ctr.kernel_launches;
             cudaGraph_t graph = nullptr;
@@ -1597,9 +1660,16 @@ void bh_step(Engine& e, float theta, float dt) {
             bh_step_body(e, w, theta, dt);
             NB_CUDA(cudaStreamEndCapture(e.stream, &graph));
             w.capturing = false;
-            NB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
+            bool updated = false;
+            if (g.exec) {
+                cudaGraphExecUpdateResultInfo info;
+                if (cudaGraphExecUpdate(g.exec, graph, &info) == cudaSuccess) updated = true;
+                else { (void)cudaGetLastError(); NB_CUDA(cudaGraphExecDestroy(g.exec)); g.exec = nullptr; }
+            }
+            if (!updated) NB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
             NB_CUDA(cudaGraphDestroy(graph));
             g.n = e.n; g.cur = cur0; g.theta = theta; g.dt = dt; g.stream = e.stream; g.arena = e.arena.base;
+            g.alloc_gen = w.alloc_gen; g.L = e.lay.L;
             g.launches = e.ctr.kernel_launches - l0;
             // the capture already advanced the host-side state exactly like a replay does below
         } else {
@@ -1607,6 +1677,9 @@ void bh_step(Engine& e, float theta, float dt) {
             e.cur ^= 1;
             w.acc_src = w.acc;
             w.last_partitioned = false;
+            TreeTable tt{};
+            tt.blk[0] = w.nblk; tt.cblk[0] = w.ncblk; tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
+            w.last_tt = tt; w.last_nparts = 1;
         }
         NB_CUDA(cudaGraphLaunch(g.exec, e.stream));
         NB_CUDA(cudaEventRecord(w.status_ev, e.stream));

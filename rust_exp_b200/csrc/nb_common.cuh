@@ -82,6 +82,31 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return r;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until *flag >= want (wrap-safe).  Bounded by timeout_ns (0 = no bound): a dead peer must not hang the GPU
+// for ever -- message + trap, which the host turns into abort().
+__device__ __forceinline__ void wait_epoch(const uint32_t* flag, uint32_t want, unsigned long long timeout_ns, int who,
+                                           const char* what) {
+    const volatile uint32_t* f = flag;
+    if (static_cast<int32_t>(*f - want) < 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (static_cast<int32_t>(*f - want) < 0) {
+            __nanosleep(100);
+            if (timeout_ns != 0ull && globaltimer_ns() - t0 > timeout_ns) {
+                printf("nbody_b200: timeout (%llu ms) waiting for rank %d to reach %s %u (at %u)\n", timeout_ns / 1000000ull, who,
+                       what, want, *f);
+                __trap();
+            }
+        }
+    }
+    __threadfence_system();
+}
+
 __device__ __forceinline__ float ld_volatile_f32(const float* p) { return *reinterpret_cast<const volatile float*>(p); }
 
 #endif  // __CUDACC__

@@ -79,20 +79,9 @@ __global__ void signal_kernel(PeerFlagPtrs peers, int world, int my_rank, uint32
     }
 }
 
-__global__ void wait_all_kernel(const uint32_t* flags, int world, uint32_t want) {
+__global__ void wait_all_kernel(const uint32_t* flags, int world, uint32_t want, unsigned long long timeout_ns) {
     const int g = threadIdx.x;
-    if (g < world) {
-        const volatile uint32_t* f = flags + g;
-        const long long t0 = clock64();
-        while (static_cast<int32_t>(*f - want) < 0) {
-            __nanosleep(200);
-            if (clock64() - t0 > 8000000000LL) {  // ~4 s: a dead peer must not hang this GPU
-                printf("nbody_b200: timeout waiting for rank %d to reach epoch %u (at %u)\n", g, want, *f);
-                __trap();
-            }
-        }
-        __threadfence_system();
-    }
+    if (g < world) wait_epoch(flags + g, want, timeout_ns, g, "epoch");
 }
 
 // mirror[g*L ..] <- peer g's current x / y / m, 16-byte vector loads over NVLink
@@ -126,15 +115,21 @@ static void ensure_mirror(Engine& e) {
     }
 }
 
+void dist_require_peers(const Engine& e) {
+    if (e.dist && e.world > 1 && !e.peers_mapped) fatal("nbx_dist_import was not called (peer arenas are not mapped)", __FILE__, __LINE__);
+}
+
 void dist_wait_all(Engine& e, uint32_t epoch) {
     if (!e.dist || e.world == 1) return;
-    wait_all_kernel<<<1, 32, 0, e.stream>>>(e.arena.flags(e.lay), e.world, epoch);
+    dist_require_peers(e);
+    wait_all_kernel<<<1, 32, 0, e.stream>>>(e.arena.flags(e.lay), e.world, epoch, e.peer_timeout_ns);
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
 }
 
 void dist_signal_step_done(Engine& e) {
     if (!e.dist || e.world == 1) return;
+    dist_require_peers(e);
     PeerFlagPtrs p{};
     for (int g = 0; g < e.world; g++) p.p[g] = e.peer[g].flags(e.lay);
     signal_kernel<<<1, 32, 0, e.stream>>>(p, e.world, e.rank, e.step_count);
@@ -159,6 +154,7 @@ void dist_gather_mirror(Engine& e, int buf) {
         e.mirror_mass_valid = true;
         return;
     }
+    dist_require_peers(e);
     dist_wait_all(e, e.step_count);
     GatherSrc s{};
     for (int g = 0; g < e.world; g++) {
@@ -187,7 +183,7 @@ void dist_fill_segments(Engine& e, AllPairsArgs& a) {
         return;
     }
     if (e.transport == NBX_TRANSPORT_P2P_DIRECT) {
-        if (!e.peers_mapped) fatal("nbx_dist_import was not called", __FILE__, __LINE__);
+        dist_require_peers(e);
         for (int g = 0; g < e.world; g++) {
             const ArenaView& av = (g == e.rank) ? e.arena : e.peer[g];
             a.seg[g] = JSeg{av.x(e.lay, buf), av.y(e.lay, buf), av.m(e.lay)};
@@ -251,6 +247,7 @@ int dist_init(Engine& e, int rank, int world, int max_particles) {
     const size_t per = (static_cast<size_t>(max_particles) + world - 1) / world;
     const size_t L = (per + kShardAlign - 1) / kShardAlign * kShardAlign;
     e.lay.set(L);
+    e.L_cap = L;
     NB_CUDA(cudaMalloc(&e.arena.base, e.lay.bytes));
     NB_CUDA(cudaMemset(e.arena.base, 0, e.lay.bytes));
     if (world > 1) {

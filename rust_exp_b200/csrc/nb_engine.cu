@@ -82,6 +82,7 @@ void ensure_init(Engine& e) {
     }
     int dev = 0;
     if (const char* s = getenv("NB_DEVICE")) dev = atoi(s);
+    if (const char* s = getenv("NB_PEER_TIMEOUT_MS")) e.peer_timeout_ns = atoll(s) <= 0 ? 0ull : static_cast<uint64_t>(atoll(s)) * 1000000ull;
     if (try_init(e, dev) != 0) fatal(g_err, __FILE__, __LINE__);
 }
 
@@ -92,6 +93,16 @@ void ensure_capacity(Engine& e, int n) {
         if (n > e.max_particles) {
             set_error("n=%d exceeds nbx_dist_init max_particles=%d", n, e.max_particles);
             fatal(g_err, __FILE__, __LINE__);
+        }
+        // Balanced shards: L follows the size of the set (ceil(n / world), 1024-aligned), not the capacity the arena
+        // was allocated for -- otherwise a set much smaller than max_particles would sit on the first ranks only.
+        // All ranks derive the same layout from the same n; the flags at offset 0 never move.
+        size_t L = ((static_cast<size_t>(n) + e.world - 1) / e.world + kShardAlign - 1) / kShardAlign * kShardAlign;
+        if (L == 0) L = kShardAlign;
+        if (L > e.L_cap) L = e.L_cap;
+        if (L != e.lay.L) {
+            NB_CUDA(cudaStreamSynchronize(e.stream));
+            e.lay.set(L);
         }
     } else {
         size_t L = (static_cast<size_t>(n) + kShardAlign - 1) / kShardAlign * kShardAlign;
@@ -118,8 +129,9 @@ void ensure_capacity(Engine& e, int n) {
 
 // ---- phase timing -------------------------------------------------------------------------------
 PhaseScope::PhaseScope(Engine& e_, int id_) : e(e_), id(id_) {
-    if (e.phase_timing && e.ev_slot < Engine::kPhaseRing) {
-        cudaEvent_t* pr = e.ev[id][e.ev_slot];
+    if (e.phase_timing && e.ev_slot < Engine::kPhaseRing && e.ev_sub[id][e.ev_slot] < Engine::kPhaseSub) {
+        sub = e.ev_sub[id][e.ev_slot]++;
+        cudaEvent_t* pr = e.ev[id][e.ev_slot][sub];
         if (!pr[0]) {
             NB_CUDA(cudaEventCreate(&pr[0]));
             NB_CUDA(cudaEventCreate(&pr[1]));
@@ -128,27 +140,32 @@ PhaseScope::PhaseScope(Engine& e_, int id_) : e(e_), id(id_) {
     }
 }
 PhaseScope::~PhaseScope() {
-    if (e.phase_timing && e.ev_slot < Engine::kPhaseRing) {
-        NB_CUDA(cudaEventRecord(e.ev[id][e.ev_slot][1], e.stream));
+    if (sub >= 0) {
+        NB_CUDA(cudaEventRecord(e.ev[id][e.ev_slot][sub][1], e.stream));
         if (e.ev_count[id] < e.ev_slot + 1) e.ev_count[id] = e.ev_slot + 1;
     }
 }
-// average ms per step of every phase since the previous call; resets the ring
+// average ms per step of every phase since the previous call (sub-intervals of a step are summed); resets the ring
 void collect_phase_times(Engine& e) {
     NB_CUDA(cudaStreamSynchronize(e.stream));
     for (int p = 0; p < NBX_NUM_PHASES; p++) {
         double sum = 0.0;
         int cnt = 0;
         for (int k = 0; k < e.ev_count[p]; k++) {
-            float ms = 0.f;
-            if (e.ev[p][k][0] && cudaEventElapsedTime(&ms, e.ev[p][k][0], e.ev[p][k][1]) == cudaSuccess) {
-                sum += ms;
-                cnt++;
+            bool any = false;
+            for (int u = 0; u < e.ev_sub[p][k]; u++) {
+                float ms = 0.f;
+                if (e.ev[p][k][u][0] && cudaEventElapsedTime(&ms, e.ev[p][k][u][0], e.ev[p][k][u][1]) == cudaSuccess) {
+                    sum += ms;
+                    any = true;
+                }
+                (void)cudaGetLastError();
             }
-            (void)cudaGetLastError();
+            if (any) cnt++;
         }
         e.phase_ms[p] = cnt ? static_cast<float>(sum / cnt) : 0.f;
         e.ev_count[p] = 0;
+        for (int k = 0; k < Engine::kPhaseRing; k++) e.ev_sub[p][k] = 0;
     }
     e.ev_slot = 0;
 }

@@ -23,13 +23,15 @@ constexpr int kFlagSlots = 64;
 //   x[2][L]  y[2][L]   ping-pong position buffers (step s reads buffer s&1, writes (s+1)&1)
 //   m[L]               masses (constant during stepping; 0 for padding slots)
 //   vx[L] vy[L]        velocities of the local shard (read by peers only for nb_get_particles)
-//   flags[kFlagSlots]  uint32 step counters written by peers (flags[r] = steps rank r has completed)
+//   flags[kFlagSlots]  uint32 step counters written by peers (flags[r] = steps rank r has completed); at offset 0
 struct ArenaLayout {
     size_t L = 0;
     size_t off_x[2] = {0, 0}, off_y[2] = {0, 0}, off_m = 0, off_vx = 0, off_vy = 0, off_flags = 0, bytes = 0;
+    // flags come FIRST: their address must not move when the shard length follows the size of the set
     void set(size_t shard_len) {
         L = shard_len;
         size_t o = 0, f = shard_len * sizeof(float);
+        off_flags = o; o += kFlagSlots * sizeof(uint32_t);
         off_x[0] = o; o += f;
         off_x[1] = o; o += f;
         off_y[0] = o; o += f;
@@ -37,7 +39,6 @@ struct ArenaLayout {
         off_m = o; o += f;
         off_vx = o; o += f;
         off_vy = o; o += f;
-        off_flags = o; o += kFlagSlots * sizeof(uint32_t);
         bytes = (o + 255) & ~size_t(255);
     }
 };
@@ -97,6 +98,7 @@ struct AllPairsArgs {
     const uint32_t* flags;
     uint32_t wait_step;
     int my_rank;
+    unsigned long long timeout_ns;   // bound on the cross-rank waits (0 = none)
 };
 
 struct Tuning {
@@ -124,7 +126,8 @@ struct Engine {
     bool dist = false;
     int transport = NBX_TRANSPORT_P2P_DIRECT;
     int max_particles = 0;  // arena capacity in the dist case
-    ArenaLayout lay;
+    size_t L_cap = 0;       // dist: shard capacity (bodies per rank) the arena was allocated and exported for
+    ArenaLayout lay;        // layout for the CURRENT set: L = balanced shard length, <= L_cap when sharded
     size_t arena_cap_bytes = 0;
     ArenaView arena;                 // own
     ArenaView peer[kMaxRanks];       // peer[rank] == arena
@@ -133,6 +136,7 @@ struct Engine {
     char* bh_arena = nullptr;        // own (sharded mode only)
     char* bh_peer[kMaxRanks] = {};   // bh_peer[rank] == bh_arena
     int bh_partition = 0;            // 0 auto, 1 force the replicated tree, >1 virtual parts on one GPU
+    uint64_t peer_timeout_ns = 30000000000ull;   // device-side waits on peers trap after this long (0 = never)
     int cur = 0;                     // current position buffer
     uint32_t step_count = 0;         // steps completed (also the cross-rank flag value)
     // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies
@@ -153,8 +157,11 @@ struct Engine {
     bool phase_timing = false;
     // ring of event pairs per phase: one slot per step since the last nbx_get_phase_ms, so the
     // caller gets the AVERAGE device time per step of every phase over its timed region
+    // a phase may be entered several times per step (the cross-rank waits are): kPhaseSub sub-intervals per slot
     static constexpr int kPhaseRing = 128;
-    cudaEvent_t ev[NBX_NUM_PHASES][kPhaseRing][2] = {};
+    static constexpr int kPhaseSub = 4;
+    cudaEvent_t ev[NBX_NUM_PHASES][kPhaseRing][kPhaseSub][2] = {};
+    unsigned char ev_sub[NBX_NUM_PHASES][kPhaseRing] = {};
     int ev_count[NBX_NUM_PHASES] = {};
     int ev_slot = 0;  // step index within the ring
     float phase_ms[NBX_NUM_PHASES] = {};
@@ -179,6 +186,7 @@ int local_count(const Engine& e);
 struct PhaseScope {
     Engine& e;
     int id;
+    int sub = -1;
     PhaseScope(Engine& e_, int id_);
     ~PhaseScope();
 };
@@ -187,6 +195,7 @@ void collect_phase_times(Engine& e);
 // nb_state.cu
 void state_upload_aos(Engine& e, const float* aos5, int n);
 void state_download_aos(Engine& e, float* aos5, int n);
+void state_download_local(Engine& e, float* aos5_full, int n);
 void launch_integrate_fast(Engine& e, const float2* partial, int nslices, float dt, bool kill);
 void launch_integrate_exact(Engine& e, const float2* force, float dt, bool kill);
 void launch_fill_zero_f32(Engine& e, float* p, size_t n);
@@ -207,6 +216,7 @@ void dist_signal_step_done(Engine& e);                 // publish step_count to 
 void dist_wait_all(Engine& e, uint32_t step);          // device-side wait for all peers
 void dist_gather_mirror(Engine& e, int buf);           // mirror <- all shards (own kernel or NCCL)
 void dist_shutdown(Engine& e);
+void dist_require_peers(const Engine& e);               // fatal unless the peers' arenas are mapped
 int dist_init(Engine& e, int rank, int world, int max_particles);
 int dist_export(Engine& e, void* out64);
 int dist_import(Engine& e, const void* all, int world);
@@ -218,7 +228,8 @@ void bh_step(Engine& e, float theta, float dt);
 void bh_accelerations(Engine& e, float theta, float2* out);
 void bh_shutdown(Engine& e);
 int bh_flatten(Engine& e, float* out9, int cap);   // FAST tree of the last BH call, oracle flatten format
-void bh_poll(Engine& e);   // fold the last Barnes-Hut step's status/counters in (synchronises)
+void bh_poll(Engine& e);
+void bh_pop_histogram(Engine& e, uint64_t* out33, bool reset);   // fold the last Barnes-Hut step's status/counters in (synchronises)
 
 // nb_3d.cu
 void x3_set(Engine& e, const float* aos7, int n);

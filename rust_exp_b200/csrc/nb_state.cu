@@ -70,6 +70,7 @@ void state_download_aos(Engine& e, float* aos5, int n) {
     // Gather every rank's shard (peers are read over NVLink through their mapped arenas).
     if (n > e.n) n = e.n;
     if (n <= 0) return;
+    dist_require_peers(e);
     ensure_stage(e, 5 * static_cast<size_t>(n));
     const int L = static_cast<int>(e.lay.L);
     for (int g = 0; g < e.world; g++) {
@@ -86,6 +87,23 @@ void state_download_aos(Engine& e, float* aos5, int n) {
     }
     NB_CUDA(cudaMemcpyAsync(aos5, e.stage_dev, 5 * sizeof(float) * static_cast<size_t>(n), cudaMemcpyDeviceToHost,
                             e.stream));
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+}
+
+// Owner-only read-back: this rank's rows [begin, begin+count) of the global AoS array, nothing else.  No peer
+// memory is touched, so it is not a collective epoch; it orders after this rank's own enqueued steps.
+void state_download_local(Engine& e, float* aos5_full, int n) {
+    const int b = local_begin(e);
+    int c = local_count(e);
+    if (b + c > n) c = n - b;
+    if (c <= 0) { NB_CUDA(cudaStreamSynchronize(e.stream)); return; }
+    ensure_stage(e, 5 * static_cast<size_t>(c));
+    soa_to_aos_kernel<<<(c + kBlk - 1) / kBlk, kBlk, 0, e.stream>>>(e.stage_dev, c, e.arena.x(e.lay, e.cur), e.arena.y(e.lay, e.cur),
+                                                                   e.arena.vx(e.lay), e.arena.vy(e.lay), e.arena.m(e.lay));
+    NB_CUDA(cudaGetLastError());
+    e.ctr.kernel_launches++;
+    NB_CUDA(cudaMemcpyAsync(aos5_full + 5 * static_cast<size_t>(b), e.stage_dev, 5 * sizeof(float) * static_cast<size_t>(c),
+                            cudaMemcpyDeviceToHost, e.stream));
     NB_CUDA(cudaStreamSynchronize(e.stream));
 }
 

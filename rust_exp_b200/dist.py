@@ -18,7 +18,8 @@ MAX_RANKS = 8  # nb_engine.h kMaxRanks
 
 @dataclass(frozen=True)
 class ShardLayout:
-    """Rank g owns global bodies [g*L, min((g+1)*L, n)); slots beyond n are zero-mass padding."""
+    """Rank g owns global bodies [g*L, min((g+1)*L, n)); slots beyond n are zero-mass padding.
+    `for_capacity` gives the layout the arenas are allocated for; `for_set(n)` the balanced one a set of n uses."""
 
     world: int
     shard_len: int  # L
@@ -32,6 +33,13 @@ class ShardLayout:
         per = (max_particles + world - 1) // world
         L = (per + SHARD_ALIGN - 1) // SHARD_ALIGN * SHARD_ALIGN
         return ShardLayout(world, L)
+
+    def for_set(self, n: int) -> "ShardLayout":
+        """Layout actually used for a set of n bodies: shards are balanced -- L = ceil(n / world) rounded up to
+        the shard granularity, capped by the capacity the arena was allocated for (nb_engine.cu::ensure_capacity)."""
+        per = (max(n, 0) + self.world - 1) // self.world
+        L = max(SHARD_ALIGN, (per + SHARD_ALIGN - 1) // SHARD_ALIGN * SHARD_ALIGN)
+        return ShardLayout(self.world, min(L, self.shard_len))
 
     def local_range(self, rank: int, n: int) -> tuple[int, int]:
         b = min(rank * self.shard_len, n)

@@ -107,6 +107,12 @@ def test_shard_layout_matches_library_arithmetic():
     assert [lay.local_range(r, 5000) for r in range(4)] == [(0, 2048), (2048, 2048), (4096, 904), (5000, 0)]
     assert sum(c for _, c in (lay.local_range(r, 5000) for r in range(4))) == 5000
     assert lay.segment_order(2) == [2, 3, 0, 1]
+    # a set smaller than the capacity is re-balanced over all ranks (shards follow n, not max_particles)
+    cap = ShardLayout.for_capacity(1 << 22, 8)
+    assert cap.shard_len == 524288 and cap.for_set(1 << 20).shard_len == 131072 and cap.for_set(1 << 22).shard_len == 524288
+    assert cap.for_set(3000).shard_len == 1024 and cap.for_set(0).shard_len == 1024
+    assert [cap.for_set(3000).local_range(r, 3000) for r in range(4)] == [(0, 1024), (1024, 1024), (2048, 952), (3000, 0)]
+    assert ShardLayout.for_capacity(1000, 2).for_set(5000).shard_len == 1024   # never beyond the capacity
     with pytest.raises(ValueError):
         ShardLayout.for_capacity(10, 9)
 
