@@ -50,6 +50,7 @@ class Oracle:
         L.ora_bh_flatten.argtypes = [vp, i32]
         L.ora_bh_flatten.restype = i32
         L.ora_bh_forces_rows.argtypes = [f, i32, i32, vp]
+        L.ora_bh_forces_rows_mt.argtypes = [f, i32, i32, vp, i32]
         L.ora_bh_count.argtypes = [f, vp, vp]
         L.ora_bh_count_mt.argtypes = [f, vp, vp, i32]
         L.ora_accel_f64_rows.argtypes = [vp, i32, vp]
@@ -126,9 +127,12 @@ class Oracle:
         assert got == n, (got, n)
         return out
 
-    def bh_forces_rows(self, theta: float, i0: int, i1: int) -> np.ndarray:
+    def bh_forces_rows(self, theta: float, i0: int, i1: int, nthreads: int = 1) -> np.ndarray:
         out = np.empty((i1 - i0, 2), dtype=np.float32)
-        self.L.ora_bh_forces_rows(theta, i0, i1, out.ctypes.data)
+        if nthreads <= 1:
+            self.L.ora_bh_forces_rows(theta, i0, i1, out.ctypes.data)
+        else:
+            self.L.ora_bh_forces_rows_mt(theta, i0, i1, out.ctypes.data, nthreads)
         return out
 
     def bh_count(self, theta: float, nthreads: int = 0) -> tuple[int, int]:

@@ -460,6 +460,31 @@ void ora_bh_forces_rows(float theta, int32_t i0, int32_t i1, float *fxy_out)
     }
 }
 
+/* rows are independent: the same forces with the row loop split over host threads (checker speed only) */
+typedef struct { int32_t lo, hi; float theta; float *out; int32_t i0; } BhRowJob;
+static void *bh_row_worker(void *arg)
+{
+    BhRowJob *j = (BhRowJob *)arg;
+    if (j->hi > j->lo) ora_bh_forces_rows(j->theta, j->lo, j->hi, j->out + 2 * (size_t)(j->lo - j->i0));
+    return NULL;
+}
+void ora_bh_forces_rows_mt(float theta, int32_t i0, int32_t i1, float *fxy_out, int32_t nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    BhRowJob *jobs = (BhRowJob *)malloc(sizeof(BhRowJob) * nthreads);
+    int32_t n = i1 - i0, per = (n + nthreads - 1) / nthreads;
+    for (int32_t t = 0; t < nthreads; t++) {
+        jobs[t].lo = i0 + (t * per < n ? t * per : n);
+        jobs[t].hi = i0 + ((t + 1) * per < n ? (t + 1) * per : n);
+        jobs[t].theta = theta; jobs[t].out = fxy_out; jobs[t].i0 = i0;
+        pthread_create(&th[t], NULL, bh_row_worker, &jobs[t]);
+    }
+    for (int32_t t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
 typedef struct { int32_t lo, hi; float theta; uint64_t inter, visited; } CountJob;
 static void *count_worker(void *arg)
 {

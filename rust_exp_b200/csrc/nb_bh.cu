@@ -51,6 +51,7 @@ struct BhStatus {
     int lvl_begin[kLevels + 3];
     int aabb_enc[4];          // ordered-int encodings of x1,y1 (min) and x2,y2 (max)
     int n_mine;
+    int n_part;               // partitioned step: bodies this part received (device-side size of its arrays)
     int n_interior;
     int n_deep;               // partitioned build: interior nodes at or below the cut level
     int n_top;                // partitioned build: interior nodes of the shared top tree
@@ -63,8 +64,8 @@ struct BhStatus {
     unsigned long long pop_hist[33];      // histogram of popcount(lane mask)
 };
 
-constexpr int kCutLevel = 5;
-constexpr int kNumCells = 1 << (2 * kCutLevel);          // 1024
+constexpr int kCutLevel = kBhCutLevel;
+constexpr int kNumCells = kBhNumCells;                   // 1024
 constexpr int kTopNodes = (kNumCells * 4 - 1) / 3;       // levels 0..kCutLevel: 1365
 constexpr int kPartShift = 22;                           // 4M blocks per part
 constexpr int kCellShift = 2 * (kLevels - kCutLevel);
@@ -76,23 +77,37 @@ struct __align__(16) CellEntry {
     float x, y, m;    // leaf record (single body, or merged group)
     int pad;
 };
+static_assert(sizeof(CellEntry) <= 64, "the BH arena reserves 64 bytes per cell entry");
 
+// The partition of the cut-level cells over the parts: part g owns cells [cut[g], cut[g+1]).  Device-resident and
+// identical on every rank (computed by every rank from the same published cell table, one step ahead).
+struct PartPlan {
+    int cut[kMaxRanks + 1];
+};
+
+// One part of the domain-partitioned step = one rank (real ranks: this process holds exactly one; virtual ranks on a
+// single GPU, nbx_bh_partition(G): this process holds all G and "peer" pointers are simply the other parts' buffers).
 struct PartBufs {
-    int cap = 0;                                   // body capacity of this part
-    int n = 0;                                     // bodies of this part this step (host copy)
-    int *sel = nullptr, *idx_sorted = nullptr;
+    bool ready = false;
+    size_t cap = 0;                   // body capacity of the destination-side arrays
+    int cap_blocks = 0;
+    size_t R = 0;                     // inbox region capacity per source
+    // source side: this part's index shard, keyed and sorted locally
+    int src_cap = 0;
     unsigned long long *keys = nullptr, *keys_sorted = nullptr;
+    int *idx = nullptr, *idx_sorted = nullptr;
+    // "arena" (peer-visible): real ranks -> pointers into the IPC arena; virtual ranks -> one cudaMalloc with the same layout
+    char* arena = nullptr;
+    bool arena_owned = false;
+    // destination side: the merged (key-sorted) bodies of this part's cells, and the build workspace over them
+    unsigned long long* mkeys = nullptr;
     float *sx = nullptr, *sy = nullptr, *sm = nullptr;
+    int* gidx = nullptr;
     double *w3 = nullptr, *p3 = nullptr, *tile_sums = nullptr;
     signed char *delta = nullptr, *dcap = nullptr;
     unsigned char* close = nullptr;
-    int *count = nullptr, *base = nullptr, *owner = nullptr;
-    int cap_blocks = 0;
-    float4* nblk = nullptr;       // in the BH arena when real ranks are used (peer-visible)
-    int4* ncblk = nullptr;
-    CellEntry* celltab = nullptr;
-    bool arena_owned = false;     // nblk/ncblk/celltab point into the IPC arena
-    BhStatus* status = nullptr;   // per part (n_deep, interactions, ...)
+    int *count = nullptr, *base = nullptr, *owner = nullptr, *itile = nullptr;
+    BhStatus* status = nullptr;       // per part: n_part, n_interior, aabb, overflow ...
 };
 
 struct TopBufs {
@@ -102,8 +117,9 @@ struct TopBufs {
     int* tchild = nullptr;        // level-kCutLevel nodes: child block or -1
     float4* blk = nullptr;        // top blocks: 1 + (kTopNodes - kNumCells) blocks
     int4* cblk = nullptr;
-    int* hist = nullptr;          // [kNumCells]
-    int* hist_host = nullptr;     // pinned
+    PartPlan* plan = nullptr;     // [2]: plan[e & 1] is the partition step e uses; step e writes plan[(e + 1) & 1]
+    bool plan_valid = false;
+    int plan_n = -1, plan_parts = -1;
 };
 
 // Block index space: (part << shift) | block.  One tree: shift = 31, part 0.  Partitioned trees: part g < world
@@ -286,52 +302,70 @@ __global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float
 // the tile sums sequentially, then a fixed in-tile scan.  blockIdx.y selects one of the 3 arrays.
 constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const double* __restrict__ in, int len, size_t stride,
-                                                                      double* __restrict__ tile_sums, int ntiles) {
-    using BR = cub::BlockReduce<double, kScanThreads>;
+// len = len_arg, or *len_dev + len_add when the length only exists on the device (partitioned step); the grid is then
+// sized for the capacity and tiles beyond the length contribute zeros.
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const T* __restrict__ in, int len_arg, const int* __restrict__ len_dev,
+                                                                      int len_add, size_t stride, T* __restrict__ tile_sums, int ntiles) {
+    using BR = cub::BlockReduce<T, kScanThreads>;
     __shared__ typename BR::TempStorage tmp;
-    const double* a = in + blockIdx.y * stride;
+    const int len = len_dev ? *len_dev + len_add : len_arg;
+    const T* a = in + blockIdx.y * stride;
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    double v = 0.0;
+    T v = T(0);
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) v += (base + k < len) ? a[base + k] : 0.0;
-    const double t = BR(tmp).Sum(v);
+    for (int k = 0; k < kScanItems; k++) v += (base + k < len) ? a[base + k] : T(0);
+    const T t = BR(tmp).Sum(v);
     if (threadIdx.x == 0) tile_sums[blockIdx.y * ntiles + blockIdx.x] = t;
 }
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(double* tile_sums, int ntiles) {
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(T* tile_sums, int ntiles) {
     // one block per array: chunks of kScanThreads tiles, fixed block-scan tree + a sequential carry
-    using BS = cub::BlockScan<double, kScanThreads>;
+    using BS = cub::BlockScan<T, kScanThreads>;
     __shared__ typename BS::TempStorage tmp;
-    __shared__ double carry;
-    double* t = tile_sums + blockIdx.x * ntiles;
-    if (threadIdx.x == 0) carry = 0.0;
+    __shared__ T carry;
+    T* t = tile_sums + blockIdx.x * ntiles;
+    if (threadIdx.x == 0) carry = T(0);
     __syncthreads();
     for (int base = 0; base < ntiles; base += kScanThreads) {
         const int i = base + threadIdx.x;
-        const double v = i < ntiles ? t[i] : 0.0;
-        double ex, total;
+        const T v = i < ntiles ? t[i] : T(0);
+        T ex, total;
         BS(tmp).ExclusiveSum(v, ex, total);
-        const double c = carry;
+        const T c = carry;
         if (i < ntiles) t[i] = c + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry = c + total;
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const double* __restrict__ in, double* __restrict__ out, int len,
-                                                                  size_t stride, const double* __restrict__ tile_offs, int ntiles) {
-    using BS = cub::BlockScan<double, kScanThreads>;
+template <typename T>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const T* __restrict__ in, T* __restrict__ out, int len_arg,
+                                                                  const int* __restrict__ len_dev, int len_add, size_t stride,
+                                                                  const T* __restrict__ tile_offs, int ntiles) {
+    using BS = cub::BlockScan<T, kScanThreads>;
     __shared__ typename BS::TempStorage tmp;
-    const double* a = in + blockIdx.y * stride;
-    double* o = out + blockIdx.y * stride;
+    const int len = len_dev ? *len_dev + len_add : len_arg;
+    if (blockIdx.x * kScanTile >= len) return;
+    const T* a = in + blockIdx.y * stride;
+    T* o = out + blockIdx.y * stride;
     const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    double v[kScanItems];
+    T v[kScanItems];
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) v[k] = (base + k < len) ? a[base + k] : 0.0;
+    for (int k = 0; k < kScanItems; k++) v[k] = (base + k < len) ? a[base + k] : T(0);
     BS(tmp).ExclusiveSum(v, v);
-    const double off = tile_offs[blockIdx.y * ntiles + blockIdx.x];
+    const T off = tile_offs[blockIdx.y * ntiles + blockIdx.x];
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) if (base + k < len) o[base + k] = off + v[k];
+}
+
+// exclusive scan of `arrays` arrays of `len` items each (plane stride `stride`), fixed association => deterministic
+template <typename T>
+static void launch_scan(cudaStream_t s, const T* in, T* out, T* tile_sums, int arrays, int len_cap, const int* len_dev, int len_add, size_t stride) {
+    const int ntiles = (len_cap + kScanTile - 1) / kScanTile;
+    scan_tile_sums_kernel<T><<<dim3(ntiles, arrays), kScanThreads, 0, s>>>(in, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
+    scan_tile_offsets_kernel<T><<<arrays, kScanThreads, 0, s>>>(tile_sums, ntiles);
+    scan_apply_kernel<T><<<dim3(ntiles, arrays), kScanThreads, 0, s>>>(in, out, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
 }
 
 // ---- build: single pass over the sorted keys, no level synchronisation ---------------------------------
@@ -369,23 +403,23 @@ __device__ __forceinline__ void add_mass_ref(float& px, float& py, float& m, flo
     }
 }
 
-// delta[i] for the pair (i, i+1), i in [0, n-1); bit 7 = "too close" flag.  delta[n-1] = sentinel -1.
+// delta[i] for the pair (i, i+1), i in [0, n-1); delta[n-1] = sentinel -1.  n = *n_dev when given (partitioned step).
 __global__ void bh_delta_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ sx,
-                                const float* __restrict__ sy, int n, signed char* __restrict__ delta,
+                                const float* __restrict__ sy, int n_arg, const int* __restrict__ n_dev, signed char* __restrict__ delta,
                                 unsigned char* __restrict__ close) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (i == n - 1) { delta[i] = -1; close[i] = 0; return; }
-    const unsigned long long x = keys[i] ^ keys[i + 1];
-    const int d = x ? (__clzll(static_cast<long long>(x)) - (64 - kKeyBits)) >> 1 : kLevels;
-    delta[i] = static_cast<signed char>(d);
-    close[i] = (fabsf(sx[i] - sx[i + 1]) < kEps && fabsf(sy[i] - sy[i + 1]) < kEps) ? 1 : 0;
+    const int n = n_dev ? *n_dev : n_arg;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (i == n - 1) { delta[i] = -1; close[i] = 0; continue; }
+        const unsigned long long x = keys[i] ^ keys[i + 1];
+        const int d = x ? (__clzll(static_cast<long long>(x)) - (64 - kKeyBits)) >> 1 : kLevels;
+        delta[i] = static_cast<signed char>(d);
+        close[i] = (fabsf(sx[i] - sx[i + 1]) < kEps && fabsf(sy[i] - sy[i + 1]) < kEps) ? 1 : 0;
+    }
 }
 
-__global__ void bh_cap_kernel(const signed char* __restrict__ delta, const unsigned char* __restrict__ close, int n,
-                              signed char* __restrict__ dcap, int* __restrict__ count) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void bh_cap_kernel(const signed char* __restrict__ delta, const unsigned char* __restrict__ close, int n_arg,
+                              const int* __restrict__ n_dev, signed char* __restrict__ dcap, int* __restrict__ count) {
+    const int n = n_dev ? *n_dev : n_arg;
     auto cap_of = [&](int j) -> int {   // capped delta of pair j (j in [-1, n-1])
         if (j < 0 || j >= n - 1) return -1;
         int d = min(static_cast<int>(delta[j]), kLevels - 1);
@@ -399,9 +433,11 @@ __global__ void bh_cap_kernel(const signed char* __restrict__ delta, const unsig
         }
         return d;
     };
-    const int c = cap_of(i), cl = cap_of(i - 1);
-    dcap[i] = static_cast<signed char>(c);
-    count[i] = max(0, c - cl);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cap_of(i), cl = cap_of(i - 1);
+        dcap[i] = static_cast<signed char>(c);
+        count[i] = max(0, c - cl);
+    }
 }
 
 struct BuildArgs {
@@ -417,7 +453,10 @@ struct BuildArgs {
     int cut_level;       // partitioned build: interior nodes at levels >= cut_level are counted in n_deep
     struct NodeInfo* info;   // EXACT parallel build: per interior node its body range, level and own record slot
     int store_sq;            // FAST: the 4th record field is s*s (the walk's opening test compares squares); EXACT: s
+    const int* n_dev;        // partitioned step: the number of bodies only exists on the device (overrides n)
+    size_t stride;           // plane stride of p3 (n + 1 for the single tree, capacity + 1 for a part)
 };
+__device__ __forceinline__ int build_n(const BuildArgs& a) { return a.n_dev ? *a.n_dev : a.n; }
 
 __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
     // id of the interior node that starts at body `first` on `level`
@@ -427,38 +466,41 @@ __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int le
 
 // owner[id] = first body of interior node id (one thread per body; bodies start 0.76 nodes on average)
 __global__ void bh_owner_kernel(const BuildArgs a, int* __restrict__ owner, BhStatus* st) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const int dhi = a.dcap[i];
-    const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
-    const int b = a.base[i];
-    for (int k = 0; k < dhi - dlo && b + k < a.cap_interior; k++) owner[b + k] = i;
-    if (a.cut_level > 0) {
-        const int deep = dhi - max(dlo, a.cut_level - 1);
-        if (deep > 0) atomicAdd(&st->n_deep, deep);
-    }
-    if (i == 0) {
-        const int total = a.base[a.n - 1];   // count[n-1] == 0
-        st->node_count = 1 + 4 * min(total, a.cap_interior);
-        st->n_interior = min(total, a.cap_interior);
-        if (total > a.cap_interior) st->overflow = 1;
-        if (dhi < 0) {
-            // no interior node at all: the root is a leaf (one body, or everything merges)
-            float cx = 0.f, cy = 0.f, mm = 0.f;
-            for (int k = 0; k < a.n; k++) add_mass_ref(cx, cy, mm, a.sx[k], a.sy[k], a.sm[k]);
-            a.nblk[0] = make_float4(cx, 0.f, 0.f, 0.f);
-            a.nblk[1] = make_float4(cy, 0.f, 0.f, 0.f);
-            a.nblk[2] = make_float4(mm, 0.f, 0.f, 0.f);
-            a.nblk[3] = make_float4(-1.f, -1.f, -1.f, -1.f);
-            a.ncblk[0] = make_int4(-1, -1, -1, -1);
+    const int n = build_n(a);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int dhi = a.dcap[i];
+        const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
+        const int b = a.base[i];
+        for (int k = 0; k < dhi - dlo && b + k < a.cap_interior; k++) owner[b + k] = i;
+        if (a.cut_level > 0) {
+            const int deep = dhi - max(dlo, a.cut_level - 1);
+            if (deep > 0) atomicAdd(&st->n_deep, deep);
+        }
+        if (i == 0) {
+            const int total = a.base[n - 1];   // count[n-1] == 0
+            st->node_count = 1 + 4 * min(total, a.cap_interior);
+            st->n_interior = min(total, a.cap_interior);
+            if (total > a.cap_interior) st->overflow = 1;
+            if (dhi < 0) {
+                // no interior node at all: the root is a leaf (one body, or everything merges)
+                float cx = 0.f, cy = 0.f, mm = 0.f;
+                for (int k = 0; k < n; k++) add_mass_ref(cx, cy, mm, a.sx[k], a.sy[k], a.sm[k]);
+                a.nblk[0] = make_float4(cx, 0.f, 0.f, 0.f);
+                a.nblk[1] = make_float4(cy, 0.f, 0.f, 0.f);
+                a.nblk[2] = make_float4(mm, 0.f, 0.f, 0.f);
+                a.nblk[3] = make_float4(-1.f, -1.f, -1.f, -1.f);
+                a.ncblk[0] = make_int4(-1, -1, -1, -1);
+            }
         }
     }
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { st->node_count = 1; st->n_interior = 0; }
 }
 
 // one thread per interior node
 __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner, const BhStatus* st) {
     const int T = st->n_interior;
-    const size_t stride = static_cast<size_t>(a.n) + 1;
+    const int n = build_n(a);
+    const size_t stride = a.stride;
     const float rx1 = ord2f(st->aabb_enc[0]), ry1 = ord2f(st->aabb_enc[1]);
     const float rx2 = ord2f(st->aabb_enc[2]), ry2 = ord2f(st->aabb_enc[3]);
     for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < T; id += gridDim.x * blockDim.x) {
@@ -478,12 +520,12 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
         // end of this cell's range: first body whose level-l prefix differs (galloping, then bisection)
         int end;
         if (l == 0) {
-            end = a.n;
+            end = n;
         } else {
             const unsigned long long pre = key >> (shift + 2);
             int lo = i + 1, step = 2;
-            int hi = min(a.n, lo + step);
-            while (hi < a.n && (a.keys[hi - 1] >> (shift + 2)) == pre) { lo = hi; step <<= 1; hi = min(a.n, lo + step); }
+            int hi = min(n, lo + step);
+            while (hi < n && (a.keys[hi - 1] >> (shift + 2)) == pre) { lo = hi; step <<= 1; hi = min(n, lo + step); }
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if ((a.keys[mid] >> (shift + 2)) == pre) lo = mid + 1; else hi = mid;
@@ -501,9 +543,9 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
             if (l == 0) { a.info[id].blk = 0; a.info[id].slot_level = 0; }
         }
         if (l == 0) {   // the root's own record
-            const double M = a.p3[a.n] - a.p3[0];
-            a.nblk[0] = make_float4(static_cast<float>((a.p3[stride + a.n] - a.p3[stride]) / M), 0.f, 0.f, 0.f);
-            a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + a.n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
+            const double M = a.p3[n] - a.p3[0];
+            a.nblk[0] = make_float4(static_cast<float>((a.p3[stride + n] - a.p3[stride]) / M), 0.f, 0.f, 0.f);
+            a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
             a.nblk[2] = make_float4(static_cast<float>(M), 0.f, 0.f, 0.f);
             const float s0 = __fsub_rn(x2, x1);
             a.nblk[3] = make_float4(a.store_sq ? __fmul_rn(s0, s0) : s0, -1.f, -1.f, -1.f);
@@ -631,14 +673,15 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 // Lanes outside an entry's mask run with theta^2 = NaN: both `q < t` and the derived open mask are then false
 // without any per-child predicate logic.
 template <bool COUNT, bool PARTS>
-__global__ void __launch_bounds__(kTravWarps * 32) bh_traverse_fast_kernel(
+__global__ void __launch_bounds__(kTravWarps * 32, 6) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
     float theta2, BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
-    unsigned* __restrict__ cell_work) {
+    unsigned* __restrict__ cell_work, const int* __restrict__ n_dev) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lanebit = 1u << lane;
+    if (n_dev) n_list = *n_dev;     // partitioned step: the size of the part's body list only exists on the device
     const int ngroups = (n_list + 31) >> 5;
     const float qnan = __int_as_float(0x7fffffff);
     const float2 eps2 = make_float2(kEps, kEps);
@@ -953,12 +996,13 @@ static int traverse_resident_blocks(Engine& e) {
 // ticket_slot: which st->tickets[] counter this launch draws its groups from (one per launch between two resets)
 static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, const float* sy, const int* idx_sorted,
                             const int* mine, int n_list, float theta, BhStatus* st, int ticket_slot = 0,
-                            const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr) {
-    const int want = (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32);
+                            const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr, const int* n_dev = nullptr) {
+    // n_dev given: n_list is only an estimate for sizing the (persistent) grid
+    const int want = std::max(1, (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32));
     const int blocks = std::min(want, traverse_resident_blocks(e));
     const bool parts = tt.shift != 31;
     const float th2 = theta * theta;
-#define NB_TRAV(C, P) bh_traverse_fast_kernel<C, P><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work)
+#define NB_TRAV(C, P) bh_traverse_fast_kernel<C, P><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev)
     if (e.bh_count) { if (parts) NB_TRAV(true, true); else NB_TRAV(true, false); }
     else { if (parts) NB_TRAV(false, true); else NB_TRAV(false, false); }
 #undef NB_TRAV
@@ -1027,7 +1071,7 @@ static GlobalPos global_positions(Engine& e) {
 static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, NodeInfo* info) {
     cudaStream_t s = e.stream;
     const int T = 256, G = (n + T - 1) / T;
-        {
+    {
         PhaseScope ps(e, 3);
         bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
         e.ctr.kernel_launches++;
@@ -1037,25 +1081,22 @@ static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, 
         size_t tb = w.cub_bytes;
         cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, s);
     }
+    const size_t stride = static_cast<size_t>(n) + 1;
     {
         PhaseScope ps(e, 6);
         bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
         e.ctr.kernel_launches++;
-        const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
-        const size_t stride = static_cast<size_t>(n) + 1;
-        scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, len, stride, w.tile_sums, ntiles);
-        scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(w.tile_sums, ntiles);
-        scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(w.w3, w.p3, len, stride, w.tile_sums, ntiles);
+        launch_scan<double>(s, w.w3, w.p3, w.tile_sums, 3, n + 1, nullptr, 0, stride);
         e.ctr.kernel_launches += 3;
     }
     {
         PhaseScope ps(e, 5);
-        bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, w.delta, w.close);
-        bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, w.dcap, w.count);
+        bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, nullptr, w.delta, w.close);
+        bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, nullptr, w.dcap, w.count);
         size_t tb = w.cub_bytes;
         cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
         BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0, info,
-                     info ? 0 : 1};
+                     info ? 0 : 1, nullptr, stride};
         bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
         bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
         e.ctr.kernel_launches += 4;
@@ -1187,51 +1228,180 @@ static void bh_forces(Engine& e, float theta) {
 }
 
 // =================================================================================================
-// Domain-partitioned Barnes-Hut (multi-GPU)
+// Domain-partitioned Barnes-Hut (multi-GPU; SURVEY.md section 8e: the ORB split + LET exchange of the brief,
+// re-designed for NVLink-connected B200s).  Per-rank work is O(N/G); no host round trip inside a step.
 //
-// The replicated tree does not scale: every rank sorts and builds all N bodies.  Here the level-kCutLevel
-// cells of the (global, reference-identical) quadtree are dealt to the ranks as contiguous Morton ranges of
-// ~N/G bodies each -- a space-filling-curve domain split at cell granularity, so that every subtree below
-// the cut belongs to exactly one rank.  A rank selects, sorts and builds ONLY the bodies of its cells
-// (same single-pass build, same global root box => the same cells the reference would make), and publishes
-// one 48-byte entry per cell (count, f64 mass moments, leaf record or child block).  The <= 341 nodes above
-// the cut are rebuilt by every rank from the G published cell tables.  No locally-essential tree is ever
-// materialised or exchanged: block indices carry a part id, and the walk follows a remote subtree IN PLACE
-// in the owning peer's HBM over NVLink -- the opening test decides which remote nodes are touched, which is
-// exactly the LET, fetched on demand.  A rank walks the bodies of its own cells (spatially compact =>
-// mostly local nodes) and scatters each acceleration to the rank that owns the body's index shard.
-// With NB_BH_PARTS=G on ONE GPU the same code runs with G "virtual ranks" (parity-tested on a single GPU).
+// The (global, reference-identical) quadtree is cut at level kCutLevel: its 1,024 cells, in Morton order, are dealt
+// to the G ranks as contiguous ranges of equal WEIGHT -- a space-filling-curve bisection, the quadtree-aligned
+// equivalent of ORB; weight = last step's measured walk cost per cell + a per-body build cost, so the split
+// follows the work, not the body count.  Every subtree below the cut then belongs to exactly one rank ("part").
+// One step, on every rank, all on the device:
+//   boxes   bounding box of the rank's own index shard -> stored into every peer's arena; min/max over the G boxes
+//           (exact: min/max do not round) is the reference's tight global AABB (rs-src/nbody.rs:388-398)
+//   keys    Morton keys of the OWN shard only (N/G bodies), CUB radix sort of (key, index) -- N/G items
+//   send    the sorted shard falls apart into G contiguous runs, one per destination part (parts are contiguous key
+//           ranges): each run is stored straight into the destination's inbox region over NVLink (key + {x,y,m,index},
+//           24 B per body -- the all-to-all-v that replaces both body migration and the LET exchange's body half)
+//   merge   a destination holds G sorted runs: every body finds its slot by ranking its key in the other G-1 runs
+//           (binary searches; ties by source rank => deterministic) -- a G-way merge without any host-known size.
+//           From here on the number of bodies of the part exists on the device only.
+//   build   the same single-pass build as the single-GPU path, over the part's bodies, in the part's block space;
+//           one 48-byte entry per owned cell is published (count, f64 moments, leaf record or child block)
+//   top     the <= 341 nodes above the cut are rebuilt by every rank from the G published cell tables -- and, from
+//           the same table + the published walk costs, the partition of the NEXT step (identical on all ranks)
+//   walk    a rank walks the bodies of its own cells.  No locally-essential tree is materialised or exchanged: block
+//           indices carry a part id and a remote subtree is followed IN PLACE in the owning peer's HBM over NVLink --
+//           the opening test decides which remote nodes are touched, which is exactly the LET, fetched on demand.
+//           Each acceleration is stored to the rank that owns the body by index (8-byte peer stores).
+//   integrate  by the index owner, as on one GPU.
+// Four device-side ordering points per step (epoch flags, bounded waits): boxes, bodies, trees, walks.
+// With nbx_bh_partition(G) on ONE GPU the same code runs with G "virtual ranks" whose "peer" pointers are local --
+// that is how the single-GPU test box covers this path bit for bit.
 // =================================================================================================
-__global__ void __launch_bounds__(256) bh_cell_hist_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ hist) {
-    __shared__ int sh[kNumCells];
-    for (int c = threadIdx.x; c < kNumCells; c += blockDim.x) sh[c] = 0;
-    __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        atomicAdd(&sh[static_cast<int>(keys[i] >> kCellShift)], 1);
-    __syncthreads();
-    for (int c = threadIdx.x; c < kNumCells; c += blockDim.x)
-        if (sh[c]) atomicAdd(&hist[c], sh[c]);
+enum { kFlagBoxes = 0, kFlagBodies = 1, kFlagTrees = 2, kFlagWalks = 3 };
+constexpr unsigned long long kBodyWeight = 8ull;   // build cost of one body in units of one walk pop (measured ratio)
+
+struct PeerArenas { char* a[kMaxRanks]; };
+
+__global__ void bhp_signal_kernel(PeerArenas peers, size_t off_flags, int row, int world, int me, uint32_t epoch) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peers.a[g] + off_flags + (static_cast<size_t>(row) * 64 + me) * sizeof(uint32_t)) = epoch;
+        __threadfence_system();
+    }
+}
+__global__ void bhp_wait_kernel(const char* arena, size_t off_flags, int row, int world, uint32_t epoch, unsigned long long timeout_ns) {
+    const int g = threadIdx.x;
+    if (g < world)
+        wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + row * 64 + g, epoch, timeout_ns, g, "Barnes-Hut epoch");
 }
 
-struct InCells {
-    const unsigned long long* keys;
-    int c0, c1;
-    __device__ bool operator()(int i) const { const int c = static_cast<int>(keys[i] >> kCellShift); return c >= c0 && c < c1; }
-};
+// my local box -> slot `me` of every peer's box table, then the "boxes" flag
+__global__ void bhp_boxes_publish_kernel(const BhStatus* st, PeerArenas peers, size_t off_aabb, size_t off_flags, int world, int me,
+                                         uint32_t epoch) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        volatile int* dst = reinterpret_cast<volatile int*>(peers.a[g] + off_aabb) + 4 * me;
+        for (int k = 0; k < 4; k++) dst[k] = st->aabb_enc[k];
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peers.a[g] + off_flags + (static_cast<size_t>(kFlagBoxes) * 64 + me) * sizeof(uint32_t)) = epoch;
+        __threadfence_system();
+    }
+}
+// wait for all G boxes, reduce (exact), store the global box where the key / build / top kernels read it
+__global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size_t off_flags, int world, uint32_t epoch,
+                                        unsigned long long timeout_ns, BhStatus* st_part, BhStatus* st_global) {
+    const int g = threadIdx.x;
+    if (g < world)
+        wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + kFlagBoxes * 64 + g, epoch, timeout_ns, g, "Barnes-Hut boxes");
+    __syncwarp();
+    if (g == 0) {
+        const volatile int* b = reinterpret_cast<const volatile int*>(arena + off_aabb);
+        int mnx = b[0], mny = b[1], mxx = b[2], mxy = b[3];
+        for (int r = 1; r < world; r++) {
+            mnx = min(mnx, b[4 * r + 0]); mny = min(mny, b[4 * r + 1]);
+            mxx = max(mxx, b[4 * r + 2]); mxy = max(mxy, b[4 * r + 3]);
+        }
+        st_part->aabb_enc[0] = mnx; st_part->aabb_enc[1] = mny; st_part->aabb_enc[2] = mxx; st_part->aabb_enc[3] = mxy;
+        st_global->aabb_enc[0] = mnx; st_global->aabb_enc[1] = mny; st_global->aabb_enc[2] = mxx; st_global->aabb_enc[3] = mxy;
+    }
+}
 
-__global__ void bh_gather_keys_kernel(const unsigned long long* __restrict__ keys, const int* __restrict__ sel, int n,
-                                      unsigned long long* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = keys[sel[i]];
+// ---- send: the key-sorted shard -> the inbox regions of the parts that own its cells --------------------------------
+struct SendArgs {
+    const unsigned long long* keys_sorted;
+    const int* idx_sorted;
+    const float *x, *y, *m;
+    int n_local, gbegin;
+    const PartPlan* plan;
+    int nparts, me;
+    PeerArenas peers;
+    size_t off_in_key, off_in_rec, off_count_in, R;
+};
+__global__ void __launch_bounds__(256) bhp_send_kernel(const SendArgs a) {
+    __shared__ int lo[kMaxRanks + 1];
+    if (threadIdx.x <= a.nparts) {
+        // first sorted body whose cut-level cell is >= cut[p]: the start of part p's run
+        const unsigned long long kmin = static_cast<unsigned long long>(a.plan->cut[threadIdx.x]) << kCellShift;
+        int l = 0, h = a.n_local;
+        while (l < h) { const int mid = (l + h) >> 1; if (a.keys_sorted[mid] < kmin) l = mid + 1; else h = mid; }
+        lo[threadIdx.x] = l;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < a.nparts)
+        reinterpret_cast<int*>(a.peers.a[threadIdx.x] + a.off_count_in)[a.me] = lo[threadIdx.x + 1] - lo[threadIdx.x];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_local; i += gridDim.x * blockDim.x) {
+        int p = 0;
+        while (p + 1 < a.nparts && i >= lo[p + 1]) p++;
+        const int j = a.idx_sorted[i];
+        const size_t slot = static_cast<size_t>(a.me) * a.R + static_cast<size_t>(i - lo[p]);
+        reinterpret_cast<unsigned long long*>(a.peers.a[p] + a.off_in_key)[slot] = a.keys_sorted[i];
+        reinterpret_cast<float4*>(a.peers.a[p] + a.off_in_rec)[slot] = make_float4(a.x[j], a.y[j], a.m[j], __int_as_float(a.gbegin + j));
+    }
+}
+
+// ---- merge: G sorted runs -> one sorted sequence, by ranking ---------------------------------------------------------
+struct MergeArgs {
+    const char* arena;
+    size_t off_in_key, off_in_rec, off_count_in, R;
+    int nparts;
+    unsigned long long* mkeys;
+    float *sx, *sy, *sm;
+    int* gidx;
+    double* w3;
+    size_t stride;
+    BhStatus* st;
+};
+__global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
+    __shared__ int cnt[kMaxRanks], off[kMaxRanks + 1];
+    if (threadIdx.x == 0) {
+        const int* ci = reinterpret_cast<const int*>(a.arena + a.off_count_in);
+        int o = 0;
+        for (int s = 0; s < a.nparts; s++) { cnt[s] = ci[s]; off[s] = o; o += cnt[s]; }
+        off[a.nparts] = o;
+        if (blockIdx.x == 0) a.st->n_part = o;
+    }
+    __syncthreads();
+    const int n = off[a.nparts];
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(a.arena + a.off_in_key);
+    const float4* recs = reinterpret_cast<const float4*>(a.arena + a.off_in_rec);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += gridDim.x * blockDim.x) {
+        if (t == n) {   // sentinel of the exclusive scans over n + 1 entries
+            a.w3[n] = 0.0; a.w3[a.stride + n] = 0.0; a.w3[2 * a.stride + n] = 0.0;
+            continue;
+        }
+        int s = 0;
+        while (s + 1 < a.nparts && t >= off[s + 1]) s++;
+        const int i = t - off[s];
+        const unsigned long long k = keys[static_cast<size_t>(s) * a.R + i];
+        int pos = i;
+        for (int r = 0; r < a.nparts; r++) {
+            if (r == s || cnt[r] == 0) continue;
+            const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
+            int l = 0, h = cnt[r];
+            if (r < s) { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] <= k) l = mid + 1; else h = mid; } }   // ties: lower source first
+            else       { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] < k) l = mid + 1; else h = mid; } }
+            pos += l;
+        }
+        const float4 rc = recs[static_cast<size_t>(s) * a.R + i];
+        a.mkeys[pos] = k;
+        a.sx[pos] = rc.x; a.sy[pos] = rc.y; a.sm[pos] = rc.z; a.gidx[pos] = __float_as_int(rc.w);
+        a.w3[pos] = rc.z;
+        a.w3[a.stride + pos] = static_cast<double>(rc.z) * rc.x;
+        a.w3[2 * a.stride + pos] = static_cast<double>(rc.z) * rc.y;
+    }
 }
 
 // one thread per level-kCutLevel cell of this part: publish its entry
-__global__ void bh_celltab_kernel(const BuildArgs a, int c0, int c1, CellEntry* __restrict__ tab) {
+__global__ void bh_celltab_kernel(const BuildArgs a, const PartPlan* plan, int part, CellEntry* __restrict__ tab) {
+    const int c0 = plan->cut[part], c1 = plan->cut[part + 1];
     const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
-    const size_t stride = static_cast<size_t>(a.n) + 1;
+    const int n = build_n(a);
+    const size_t stride = a.stride;
     auto lb = [&](unsigned long long cell) {   // first sorted body whose cell index is >= cell
-        int lo = 0, hi = a.n;
+        int lo = 0, hi = n;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if ((a.keys[mid] >> kCellShift) < cell) lo = mid + 1; else hi = mid; }
         return lo;
     };
@@ -1265,7 +1435,9 @@ __global__ void bh_celltab_kernel(const BuildArgs a, int c0, int c1, CellEntry* 
 
 struct TopArgs {
     const CellEntry* tab[kMaxRanks];   // tab[g] valid for cells [cut[g], cut[g+1])
-    int cut[kMaxRanks + 1];
+    const unsigned* work[kMaxRanks];   // work[g][c] = walk cost rank g measured for cell c on the previous step
+    const PartPlan* plan;              // this step's partition
+    PartPlan* plan_next;               // next step's, computed here from the same data on every rank
     int nparts;
     int* tcount; double* tm3; float4* tleaf; int* tchild;
     float4* blk; int4* cblk;
@@ -1285,23 +1457,38 @@ __device__ __forceinline__ float cell_width(const BhStatus* st, int level, int p
     return __fsub_rn(x2, x1);
 }
 
-// one block: rebuild the nodes above the cut from the published cell tables (identical on every rank)
+// one block: rebuild the nodes above the cut from the published cell tables (identical on every rank), and derive
+// the next step's partition: contiguous cell ranges of equal weight (walk cost + kBodyWeight per body)
 __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhStatus* st) {
     const int tid = threadIdx.x;
     const int offk = top_off_level(kCutLevel);
+    __shared__ unsigned long long wts[kNumCells];
+    __shared__ int s_top;
     for (int c = tid; c < kNumCells; c += blockDim.x) {
         int g = 0;
-        while (g + 1 < a.nparts && c >= a.cut[g + 1]) g++;
+        while (g + 1 < a.nparts && c >= a.plan->cut[g + 1]) g++;
         const CellEntry en = a.tab[g][c];
         a.tcount[offk + c] = en.count;
         a.tm3[offk + c] = en.M; a.tm3[kTopNodes + offk + c] = en.MX; a.tm3[2 * kTopNodes + offk + c] = en.MY;
         a.tleaf[offk + c] = make_float4(en.x, en.y, en.m, 0.f);
         a.tchild[offk + c] = en.child;
+        unsigned long long wt = kBodyWeight * static_cast<unsigned long long>(en.count);
+        for (int r = 0; r < a.nparts; r++) wt += a.work[r][c];
+        wts[c] = wt;
     }
-    __syncthreads();
-    __shared__ int s_top;
     if (tid == 0) s_top = 0;
     __syncthreads();
+    if (tid == 32) {   // a second warp: the next partition, while warp 0 goes on with the tree
+        unsigned long long total = 0, cum = 0;
+        for (int c = 0; c < kNumCells; c++) total += wts[c];
+        int g = 1;
+        a.plan_next->cut[0] = 0;
+        for (int c = 0; c < kNumCells; c++) {
+            while (g < a.nparts && cum * a.nparts >= static_cast<unsigned long long>(g) * total) a.plan_next->cut[g++] = c;
+            cum += wts[c];
+        }
+        while (g <= a.nparts) a.plan_next->cut[g++] = kNumCells;
+    }
     for (int l = kCutLevel - 1; l >= 0; l--) {
         const int off = top_off_level(l), offc = top_off_level(l + 1);
         for (int p = tid; p < (1 << (2 * l)); p += blockDim.x) {
@@ -1362,44 +1549,69 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
     }
 }
 
-// ---- partitioned step: host side -------------------------------------------------------------------------
-__global__ void bh_flag_signal_kernel(PeerU32 peers, int world, int slot, uint32_t value) {
-    const int g = threadIdx.x;
-    if (g < world) {
-        __threadfence_system();
-        *reinterpret_cast<volatile uint32_t*>(peers.p[g] + slot) = value;
-        __threadfence_system();
+struct PartStatusPtrs { BhStatus* p[kMaxRanks]; };
+__global__ void bhp_fold_status_kernel(BhStatus* global, PartStatusPtrs parts, int nlocal) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int deep = 0, ovf = 0;
+        for (int r = 0; r < nlocal; r++) { deep += parts.p[r]->n_deep; ovf |= parts.p[r]->overflow; }
+        global->n_deep += deep;
+        global->overflow |= ovf;
     }
 }
-__global__ void bh_flag_wait_kernel(const uint32_t* flags, int world, uint32_t want, unsigned long long timeout_ns) {
-    const int g = threadIdx.x;
-    if (g < world) wait_epoch(flags + g, want, timeout_ns, g, "Barnes-Hut epoch");
+__global__ void bhp_plan_init_kernel(PartPlan* plan2, int nparts) {
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        for (int b = 0; b < 2; b++)
+            for (int g = 0; g <= nparts; g++) plan2[b].cut[g] = static_cast<int>(static_cast<long long>(g) * kNumCells / nparts);
 }
 
-static void part_ensure(Engine& e, BhWork& w, PartBufs& P, int n, bool in_arena) {
-    if (n <= P.cap) return;
-    NB_CUDA(cudaStreamSynchronize(e.stream));
+// ---- partitioned step: host side -------------------------------------------------------------------------
+static void part_free(PartBufs& P) {
     auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(P.sel); fr(P.idx_sorted); fr(P.keys); fr(P.keys_sorted); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.w3); fr(P.p3);
-    fr(P.tile_sums); fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner);
-    const size_t N = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 1024;   // headroom: partitions drift
-    NB_CUDA(cudaMalloc(&P.sel, N * 4)); NB_CUDA(cudaMalloc(&P.idx_sorted, N * 4));
-    NB_CUDA(cudaMalloc(&P.keys, N * 8)); NB_CUDA(cudaMalloc(&P.keys_sorted, N * 8));
-    NB_CUDA(cudaMalloc(&P.sx, N * 4)); NB_CUDA(cudaMalloc(&P.sy, N * 4)); NB_CUDA(cudaMalloc(&P.sm, N * 4));
+    fr(P.keys); fr(P.keys_sorted); fr(P.idx); fr(P.idx_sorted);
+    fr(P.mkeys); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.gidx); fr(P.w3); fr(P.p3); fr(P.tile_sums);
+    fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner); fr(P.itile); fr(P.status);
+    if (P.arena_owned) fr(P.arena);
+    P = PartBufs();
+}
+
+// (re)allocate one part: src_cap bodies on the source side, cap bodies on the destination side
+static void part_ensure(Engine& e, BhWork& w, PartBufs& P, int src_cap, size_t cap, const BhArenaLayout& lay, char* ipc_arena) {
+    if (P.ready && src_cap <= P.src_cap && cap <= P.cap && lay.R == P.R && lay.cap_blocks == P.cap_blocks &&
+        (ipc_arena == nullptr || ipc_arena == P.arena)) return;
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    part_free(P);
+    const size_t S = static_cast<size_t>(src_cap), N = cap;
+    NB_CUDA(cudaMalloc(&P.keys, S * 8)); NB_CUDA(cudaMalloc(&P.keys_sorted, S * 8));
+    NB_CUDA(cudaMalloc(&P.idx, S * 4)); NB_CUDA(cudaMalloc(&P.idx_sorted, S * 4));
+    NB_CUDA(cudaMalloc(&P.mkeys, N * 8));
+    NB_CUDA(cudaMalloc(&P.sx, N * 4)); NB_CUDA(cudaMalloc(&P.sy, N * 4)); NB_CUDA(cudaMalloc(&P.sm, N * 4)); NB_CUDA(cudaMalloc(&P.gidx, N * 4));
     NB_CUDA(cudaMalloc(&P.w3, 3 * (N + 1) * 8)); NB_CUDA(cudaMalloc(&P.p3, 3 * (N + 1) * 8));
-    NB_CUDA(cudaMalloc(&P.tile_sums, 3 * ((N + 1 + kScanTile - 1) / kScanTile) * 8));
+    const size_t ntiles = (N + 1 + kScanTile - 1) / kScanTile;
+    NB_CUDA(cudaMalloc(&P.tile_sums, 3 * ntiles * 8)); NB_CUDA(cudaMalloc(&P.itile, ntiles * 4));
     NB_CUDA(cudaMalloc(&P.delta, N)); NB_CUDA(cudaMalloc(&P.dcap, N)); NB_CUDA(cudaMalloc(&P.close, N));
     NB_CUDA(cudaMalloc(&P.count, N * 4)); NB_CUDA(cudaMalloc(&P.base, N * 4));
-    if (!in_arena) {
-        fr(P.nblk); fr(P.ncblk); fr(P.celltab);
-        P.cap_blocks = static_cast<int>(std::min<size_t>(2 * N + 4096, (1u << kPartShift) - 1));
-        NB_CUDA(cudaMalloc(&P.nblk, sizeof(float4) * 4 * static_cast<size_t>(P.cap_blocks)));
-        NB_CUDA(cudaMalloc(&P.ncblk, sizeof(int4) * static_cast<size_t>(P.cap_blocks)));
-        NB_CUDA(cudaMalloc(&P.celltab, sizeof(CellEntry) * kNumCells));
+    NB_CUDA(cudaMalloc(&P.owner, sizeof(int) * static_cast<size_t>(lay.cap_blocks)));
+    NB_CUDA(cudaMalloc(&P.status, sizeof(BhStatus)));
+    NB_CUDA(cudaMemset(P.status, 0, sizeof(BhStatus)));
+    if (ipc_arena) {
+        P.arena = ipc_arena;
+        P.arena_owned = false;
+    } else {
+        NB_CUDA(cudaMalloc(&P.arena, lay.bytes));
+        NB_CUDA(cudaMemset(P.arena, 0, lay.off_in_key));   // flags, boxes, counts, walk costs, cell table
+        P.arena_owned = true;
     }
-    NB_CUDA(cudaMalloc(&P.owner, sizeof(int) * static_cast<size_t>(P.cap_blocks)));
-    P.cap = static_cast<int>(N);
-    (void)w;
+    P.src_cap = src_cap; P.cap = cap; P.cap_blocks = lay.cap_blocks; P.R = lay.R;
+    P.ready = true;
+    w.alloc_gen++;
+    // the source-side sort needs CUB scratch for src_cap items
+    size_t b1 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b1, P.keys, P.keys_sorted, P.idx, P.idx_sorted, src_cap, 0, kKeyBits, e.stream);
+    if (b1 + 256 > w.cub_bytes) {
+        if (w.cub_tmp) NB_CUDA(cudaFree(w.cub_tmp));
+        w.cub_bytes = b1 + 256;
+        NB_CUDA(cudaMalloc(&w.cub_tmp, w.cub_bytes));
+    }
 }
 
 static void top_ensure(TopBufs& t) {
@@ -1410,140 +1622,168 @@ static void top_ensure(TopBufs& t) {
     NB_CUDA(cudaMalloc(&t.tchild, sizeof(int) * kTopNodes));
     NB_CUDA(cudaMalloc(&t.blk, sizeof(float4) * 4 * (kTopNodes + 1)));
     NB_CUDA(cudaMalloc(&t.cblk, sizeof(int4) * (kTopNodes + 1)));
-    NB_CUDA(cudaMalloc(&t.hist, sizeof(int) * kNumCells));
-    NB_CUDA(cudaMallocHost(&t.hist_host, sizeof(int) * kNumCells));
-}
-
-// sort + build the subtree forest of one part (bodies whose level-kCutLevel cell lies in [c0, c1))
-static void build_part(Engine& e, BhWork& w, PartBufs& P, const GlobalPos& gp, int n_all, int c0, int c1, int part_id) {
-    cudaStream_t s = e.stream;
-    const int T = 256;
-    const int n = P.n;
-    if (n > 0) {
-        size_t tb = w.cub_bytes;
-        cub::DeviceSelect::If(w.cub_tmp, tb, Iota(0), P.sel, &w.status->n_mine, n_all, InCells{w.keys, c0, c1}, s);
-        const int G = (n + T - 1) / T;
-        bh_gather_keys_kernel<<<G, T, 0, s>>>(w.keys, P.sel, n, P.keys);
-        tb = w.cub_bytes;
-        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, P.keys, P.keys_sorted, P.sel, P.idx_sorted, n, 0, kKeyBits, s);
-        bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, P.idx_sorted, n, P.sx, P.sy, P.sm, P.w3);
-        const int len = n + 1, ntiles = (len + kScanTile - 1) / kScanTile;
-        const size_t stride = static_cast<size_t>(n) + 1;
-        scan_tile_sums_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(P.w3, len, stride, P.tile_sums, ntiles);
-        scan_tile_offsets_kernel<<<3, kScanThreads, 0, s>>>(P.tile_sums, ntiles);
-        scan_apply_kernel<<<dim3(ntiles, 3), kScanThreads, 0, s>>>(P.w3, P.p3, len, stride, P.tile_sums, ntiles);
-        bh_delta_kernel<<<G, T, 0, s>>>(P.keys_sorted, P.sx, P.sy, n, P.delta, P.close);
-        bh_cap_kernel<<<G, T, 0, s>>>(P.delta, P.close, n, P.dcap, P.count);
-        tb = w.cub_bytes;
-        cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, P.count, P.base, n, s);
-        e.ctr.kernel_launches += 8;
-    }
-    BuildArgs ba{P.keys_sorted, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, P.nblk, P.ncblk, n, P.cap_blocks - 2,
-                 static_cast<unsigned>(part_id) << kPartShift, kCutLevel, nullptr, 1};
-    if (n > 0) {
-        const int G = (n + T - 1) / T;
-        bh_owner_kernel<<<G, T, 0, s>>>(ba, P.owner, w.status);
-        bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, P.owner, w.status);
-        e.ctr.kernel_launches += 2;
-    }
-    if (c1 > c0) {
-        bh_celltab_kernel<<<(c1 - c0 + 127) / 128, 128, 0, s>>>(ba, c0, c1, P.celltab);
-        e.ctr.kernel_launches++;
-    }
-    NB_CUDA(cudaGetLastError());
+    NB_CUDA(cudaMalloc(&t.plan, sizeof(PartPlan) * 2));
 }
 
 static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     BhWork& w = work(e);
-    const bool real = e.dist && e.world > 1;      // real ranks: this process builds part e.rank only
+    const bool real = e.dist && e.world > 1;      // real ranks: this process is part e.rank only
     const int n = e.n;
-    const int nl = local_count(e);
-    const GlobalPos gp = global_positions(e);     // sharded: gathers all positions first (epoch-ordered)
     cudaStream_t s = e.stream;
-    const int T = 256, G = (n + T - 1) / T;
+    const int T = 256;
     top_ensure(w.top);
+    // ---- geometry of the parts this process runs ----------------------------------------------------------------
+    const int nlocal = real ? 1 : nparts;
+    BhArenaLayout vlay;                              // virtual ranks: a private layout sized for this set
+    size_t shard = e.lay.L;                          // index-shard length: owner of body i is i / shard
+    if (!real) {
+        shard = ((static_cast<size_t>(n) + nparts - 1) / nparts + kShardAlign - 1) / kShardAlign * kShardAlign;
+        vlay.set(shard, nparts, static_cast<size_t>(n));
+    }
+    const BhArenaLayout& lay = real ? e.bh_lay : vlay;
+    if (static_cast<int>(w.parts.size()) != nlocal) {
+        NB_CUDA(cudaStreamSynchronize(s));
+        for (PartBufs& P : w.parts) part_free(P);
+        w.parts.assign(nlocal, PartBufs());
+    }
+    for (int r = 0; r < nlocal; r++)
+        part_ensure(e, w, w.parts[r], static_cast<int>(real ? e.L_cap : shard), real ? static_cast<size_t>(e.max_particles) : static_cast<size_t>(n),
+                    lay, real ? e.bh_arena : nullptr);
+    PeerArenas peers{};
+    for (int g = 0; g < nparts; g++) peers.a[g] = real ? e.bh_peer[g] : w.parts[g].arena;
+    if (real) dist_require_peers(e);
+    if (!w.top.plan_valid || w.top.plan_n != n || w.top.plan_parts != nparts) {
+        bhp_plan_init_kernel<<<1, 32, 0, s>>>(w.top.plan, nparts);   // bootstrap: equal cell ranges; balanced from the next step on
+        w.top.plan_valid = true; w.top.plan_n = n; w.top.plan_parts = nparts;
+        for (int r = 0; r < nlocal; r++)
+            NB_CUDA(cudaMemsetAsync(w.parts[r].arena + lay.off_cellwork, 0, 2 * kNumCells * sizeof(unsigned), s));
+        e.ctr.kernel_launches++;
+    }
+    const uint32_t epoch = ++w.bh_epoch;
+    const PartPlan* plan = w.top.plan + (epoch & 1u);
+    PartPlan* plan_next = w.top.plan + ((epoch + 1u) & 1u);
+    auto part_id = [&](int r) { return real ? e.rank : r; };
+    auto src_begin = [&](int r) { return real ? local_begin(e) : static_cast<int>(std::min<size_t>(static_cast<size_t>(r) * shard, static_cast<size_t>(n))); };
+    auto src_count = [&](int r) {
+        if (real) return local_count(e);
+        const long long b = static_cast<long long>(r) * static_cast<long long>(shard);
+        return static_cast<int>(std::max<long long>(0, std::min<long long>(static_cast<long long>(shard), n - b)));
+    };
+    auto src_x = [&](int r) { return e.arena.x(e.lay, e.cur) + (real ? 0 : src_begin(r)); };
+    auto src_y = [&](int r) { return e.arena.y(e.lay, e.cur) + (real ? 0 : src_begin(r)); };
+    auto src_m = [&](int r) { return e.arena.m(e.lay) + (real ? 0 : src_begin(r)); };
+    // ---- boxes ------------------------------------------------------------------------------------------------------
     {
         PhaseScope ps(e, 2);
         bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
-        bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
-        e.ctr.kernel_launches += 2;
+        e.ctr.kernel_launches++;
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            const int nl = src_count(r);
+            bh_reset_kernel<<<1, 32, 0, s>>>(P.status);
+            if (nl > 0) bh_aabb_kernel<<<std::min((nl + T - 1) / T, e.num_sms * 4), T, 0, s>>>(src_x(r), src_y(r), nl, P.status);
+            NB_CUDA(cudaMemsetAsync(P.arena + lay.off_cellwork + (epoch & 1u) * kNumCells * sizeof(unsigned), 0, kNumCells * sizeof(unsigned), s));
+            bhp_boxes_publish_kernel<<<1, 32, 0, s>>>(P.status, peers, lay.off_aabb, lay.off_flags, nparts, part_id(r), epoch);
+            e.ctr.kernel_launches += 3;
+        }
     }
+    {
+        PhaseScope ps(e, 7);
+        for (int r = 0; r < nlocal; r++) {
+            bhp_boxes_reduce_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_aabb, lay.off_flags, nparts, epoch, e.peer_timeout_ns,
+                                                     w.parts[r].status, w.status);
+            e.ctr.kernel_launches++;
+        }
+    }
+    // ---- keys + sort of the own shard ----------------------------------------------------------------------------------
     {
         PhaseScope ps(e, 3);
-        bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
-        NB_CUDA(cudaMemsetAsync(w.top.hist, 0, sizeof(int) * kNumCells, s));
-        bh_cell_hist_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(w.keys, n, w.top.hist);
-        e.ctr.kernel_launches += 2;
-        // the only host round trip of the step: 4 KB of cell counts -> the partition (identical on all ranks)
-        NB_CUDA(cudaMemcpyAsync(w.top.hist_host, w.top.hist, sizeof(int) * kNumCells, cudaMemcpyDeviceToHost, s));
-        NB_CUDA(cudaStreamSynchronize(s));
+        for (int r = 0; r < nlocal; r++) {
+            const int nl = src_count(r);
+            if (nl > 0) { bh_keys_kernel<<<(nl + T - 1) / T, T, 0, s>>>(src_x(r), src_y(r), nl, w.parts[r].status, w.parts[r].keys, w.parts[r].idx); e.ctr.kernel_launches++; }
+        }
     }
-    int cut[kMaxRanks + 1], cnt[kMaxRanks];
     {
-        long long cum = 0;
-        int g = 1;
-        cut[0] = 0;
-        for (int c = 0; c < kNumCells; c++) {
-            while (g < nparts && cum * nparts >= static_cast<long long>(g) * n) cut[g++] = c;
-            cum += w.top.hist_host[c];
-        }
-        while (g <= nparts) cut[g++] = kNumCells;
-        for (int r = 0; r < nparts; r++) {
-            long long c2 = 0;
-            for (int c = cut[r]; c < cut[r + 1]; c++) c2 += w.top.hist_host[c];
-            cnt[r] = static_cast<int>(c2);
+        PhaseScope ps(e, 4);
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            const int nl = src_count(r);
+            if (nl > 0) {
+                size_t tb = w.cub_bytes;
+                cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, nl, 0, kKeyBits, s);
+            }
         }
     }
-    if (static_cast<int>(w.parts.size()) != (real ? 1 : nparts)) w.parts.resize(real ? 1 : nparts);
-    const uint32_t epoch = ++w.bh_epoch;
+    // ---- send + merge ---------------------------------------------------------------------------------------------------
+    {
+        PhaseScope ps(e, 7);
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            const int nl = src_count(r);
+            SendArgs sa{P.keys_sorted, P.idx_sorted, src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan, nparts, part_id(r), peers,
+                        lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R};
+            bhp_send_kernel<<<std::max(1, std::min((nl + T - 1) / T, e.num_sms * 8)), T, 0, s>>>(sa);
+            bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagBodies, nparts, part_id(r), epoch);
+            e.ctr.kernel_launches += 2;
+        }
+        for (int r = 0; r < nlocal; r++) {
+            bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagBodies, nparts, epoch, e.peer_timeout_ns);
+            e.ctr.kernel_launches++;
+        }
+    }
+    const int est = static_cast<int>(std::min<size_t>(real ? static_cast<size_t>(e.max_particles) : static_cast<size_t>(n),
+                                                      2 * ((static_cast<size_t>(n) + nparts - 1) / nparts) + 4096));   // grid sizing only
+    const int GE = std::max(1, std::min((est + T - 1) / T, e.num_sms * 16));
+    {
+        PhaseScope ps(e, 6);
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            const size_t stride = P.cap + 1;
+            MergeArgs ma{P.arena, lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R, nparts, P.mkeys, P.sx, P.sy, P.sm, P.gidx, P.w3, stride, P.status};
+            bhp_merge_kernel<<<GE, T, 0, s>>>(ma);
+            launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride);
+            e.ctr.kernel_launches += 4;
+        }
+    }
+    // ---- build of the part's subtree forest + its cell table ---------------------------------------------------------------
     {
         PhaseScope ps(e, 5);
-        for (int r = 0; r < nparts; r++) {
-            if (real && r != e.rank) continue;
-            PartBufs& P = w.parts[real ? 0 : r];
-            if (real && !P.arena_owned) {
-                P.nblk = reinterpret_cast<float4*>(e.bh_arena + e.bh_lay.off_nblk);
-                P.ncblk = reinterpret_cast<int4*>(e.bh_arena + e.bh_lay.off_ncblk);
-                P.celltab = reinterpret_cast<CellEntry*>(e.bh_arena + e.bh_lay.off_celltab);
-                P.cap_blocks = e.bh_lay.cap_blocks;
-                P.arena_owned = true;
-            }
-            part_ensure(e, w, P, std::max(cnt[r], 1), real);
-            P.n = cnt[r];
-            build_part(e, w, P, gp, n, cut[r], cut[r + 1], r);
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            const int* nd = &P.status->n_part;
+            bh_delta_kernel<<<GE, T, 0, s>>>(P.mkeys, P.sx, P.sy, 0, nd, P.delta, P.close);
+            bh_cap_kernel<<<GE, T, 0, s>>>(P.delta, P.close, 0, nd, P.dcap, P.count);
+            launch_scan<int>(s, P.count, P.base, P.itile, 1, static_cast<int>(P.cap), nd, 0, 0);
+            BuildArgs ba{P.mkeys, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, reinterpret_cast<float4*>(P.arena + lay.off_nblk),
+                         reinterpret_cast<int4*>(P.arena + lay.off_ncblk), 0, P.cap_blocks - 2,
+                         static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, 1, nd, P.cap + 1};
+            bh_owner_kernel<<<GE, T, 0, s>>>(ba, P.owner, P.status);
+            bh_emit_kernel<<<std::min(GE, e.num_sms * 8), T, 0, s>>>(ba, P.owner, P.status);
+            bh_celltab_kernel<<<(kNumCells + 127) / 128, 128, 0, s>>>(ba, plan, part_id(r), reinterpret_cast<CellEntry*>(P.arena + lay.off_celltab));
+            e.ctr.kernel_launches += 8;
         }
     }
-    TopArgs ta{};
+    {
+        PhaseScope ps(e, 7);
+        for (int r = 0; r < nlocal; r++) { bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagTrees, nparts, part_id(r), epoch); e.ctr.kernel_launches++; }
+        for (int r = 0; r < nlocal; r++) { bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagTrees, nparts, epoch, e.peer_timeout_ns); e.ctr.kernel_launches++; }
+    }
+    // ---- top tree (+ the next partition), then the walk ------------------------------------------------------------------
     TreeTable tt{};
     tt.shift = kPartShift;
     tt.root = static_cast<unsigned>(kMaxRanks) << kPartShift;
-    tt.shard_len = static_cast<int>(e.lay.L);
-    for (int r = 0; r <= nparts; r++) ta.cut[r] = cut[r];
-    ta.nparts = nparts;
-    if (real) {
-        PhaseScope ps(e, 7);
-        // publish "my subtrees and cell table are ready", then wait for everybody's
-        PeerU32 pf{};
-        for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags);
-        bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
-        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags), e.world, epoch, e.peer_timeout_ns);
-        e.ctr.kernel_launches += 2;
-        for (int g = 0; g < e.world; g++) {
-            ta.tab[g] = reinterpret_cast<const CellEntry*>(e.bh_peer[g] + e.bh_lay.off_celltab);
-            tt.blk[g] = reinterpret_cast<const float4*>(e.bh_peer[g] + e.bh_lay.off_nblk);
-            tt.cblk[g] = reinterpret_cast<const int4*>(e.bh_peer[g] + e.bh_lay.off_ncblk);
-            tt.acc[g] = reinterpret_cast<float2*>(e.bh_peer[g] + e.bh_lay.off_acc);
-        }
-    } else {
-        for (int r = 0; r < nparts; r++) {
-            ta.tab[r] = w.parts[r].celltab;
-            tt.blk[r] = w.parts[r].nblk;
-            tt.cblk[r] = w.parts[r].ncblk;
-        }
-        for (int g = 0; g < kMaxRanks; g++) tt.acc[g] = w.acc;
-    }
+    tt.shard_len = static_cast<int>(shard);
     {
         PhaseScope ps(e, 6);
+        TopArgs ta{};
+        for (int g = 0; g < nparts; g++) {
+            ta.tab[g] = reinterpret_cast<const CellEntry*>(peers.a[g] + lay.off_celltab);
+            ta.work[g] = reinterpret_cast<const unsigned*>(peers.a[g] + lay.off_cellwork) + ((epoch + 1u) & 1u) * kNumCells;   // previous step's
+            tt.blk[g] = reinterpret_cast<const float4*>(peers.a[g] + lay.off_nblk);
+            tt.cblk[g] = reinterpret_cast<const int4*>(peers.a[g] + lay.off_ncblk);
+            tt.acc[g] = real ? reinterpret_cast<float2*>(peers.a[g] + lay.off_acc) : (w.acc + static_cast<size_t>(g) * shard);
+        }
+        ta.plan = plan; ta.plan_next = plan_next; ta.nparts = nparts;
         ta.tcount = w.top.tcount; ta.tm3 = w.top.tm3; ta.tleaf = w.top.tleaf; ta.tchild = w.top.tchild;
         ta.blk = w.top.blk; ta.cblk = w.top.cblk;
         ta.top_off = static_cast<unsigned>(kMaxRanks) << kPartShift;
@@ -1554,26 +1794,24 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     }
     {
         PhaseScope ps(e, 0);
-        for (int r = 0; r < nparts; r++) {
-            if (real && r != e.rank) continue;
-            PartBufs& P = w.parts[real ? 0 : r];
-            if (P.n > 0) launch_traverse(e, tt, P.sx, P.sy, P.idx_sorted, nullptr, P.n, theta, w.status, real ? 0 : r);
+        for (int r = 0; r < nlocal; r++) {
+            PartBufs& P = w.parts[r];
+            launch_traverse(e, tt, P.sx, P.sy, P.gidx, nullptr, est, theta, w.status, real ? 0 : r, P.mkeys,
+                            reinterpret_cast<unsigned*>(P.arena + lay.off_cellwork) + (epoch & 1u) * kNumCells, &P.status->n_part);
         }
     }
-    if (real) {
+    {
         PhaseScope ps(e, 7);
-        // accelerations were scattered to their owners over NVLink: publish "my walk is done" and wait until
-        // every rank's walk is done (=> my acc buffer is complete and nobody reads my subtrees any more)
-        PeerU32 pf{};
-        for (int g = 0; g < e.world; g++) pf.p[g] = reinterpret_cast<uint32_t*>(e.bh_peer[g] + e.bh_lay.off_flags) + kMaxRanks;
-        bh_flag_signal_kernel<<<1, 32, 0, s>>>(pf, e.world, e.rank, epoch);
-        bh_flag_wait_kernel<<<1, 32, 0, s>>>(reinterpret_cast<uint32_t*>(e.bh_arena + e.bh_lay.off_flags) + kMaxRanks, e.world, epoch, e.peer_timeout_ns);
-        e.ctr.kernel_launches += 2;
-        w.acc_src = reinterpret_cast<float2*>(e.bh_arena + e.bh_lay.off_acc);
-    } else {
-        w.acc_src = w.acc;
+        // accelerations were stored to their index owners (over NVLink): publish "my walk is done" and wait until every
+        // rank's is (=> my acc buffer is complete, nobody reads my subtrees any more, the inboxes may be overwritten)
+        for (int r = 0; r < nlocal; r++) { bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagWalks, nparts, part_id(r), epoch); e.ctr.kernel_launches++; }
+        for (int r = 0; r < nlocal; r++) { bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagWalks, nparts, epoch, e.peer_timeout_ns); e.ctr.kernel_launches++; }
     }
-    (void)nl;
+    PartStatusPtrs sp{};
+    for (int r = 0; r < nlocal; r++) sp.p[r] = w.parts[r].status;
+    bhp_fold_status_kernel<<<1, 32, 0, s>>>(w.status, sp, nlocal);
+    e.ctr.kernel_launches++;
+    w.acc_src = real ? reinterpret_cast<float2*>(e.bh_arena + lay.off_acc) : w.acc;
     w.last_partitioned = true;
     w.last_tt = tt; w.last_nparts = nparts;
     NB_CUDA(cudaGetLastError());
@@ -1729,7 +1967,7 @@ int bh_flatten(Engine& e, float* out9, int cap) {
         fetch(0, static_cast<size_t>(h.n_interior) + 1);
     } else {
         if (e.dist && e.world > 1) return -1;   // peers' arrays are not fetched here: single-process (virtual ranks) only
-        for (int r = 0; r < w.last_nparts; r++) fetch(r, static_cast<size_t>(w.parts[r].cap_blocks));
+        for (int r = 0; r < w.last_nparts; r++) fetch(r, static_cast<size_t>(w.parts[r].cap_blocks));   // virtual ranks: local arrays
         fetch(kMaxRanks, kTopNodes + 1);
     }
     auto ord2f_h = [](int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; };
@@ -1777,13 +2015,8 @@ void bh_shutdown(Engine& e) {
     if (w.status_host) cudaFreeHost(w.status_host);
     if (w.status_ev) cudaEventDestroy(w.status_ev);
     for (auto& g : w.graph) if (g.exec) cudaGraphExecDestroy(g.exec);
-    for (PartBufs& P : w.parts) {
-        fr(P.sel); fr(P.idx_sorted); fr(P.keys); fr(P.keys_sorted); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.w3); fr(P.p3);
-        fr(P.tile_sums); fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner);
-        if (!P.arena_owned) { fr(P.nblk); fr(P.ncblk); fr(P.celltab); }
-    }
-    fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.hist);
-    if (w.top.hist_host) cudaFreeHost(w.top.hist_host);
+    for (PartBufs& P : w.parts) part_free(P);
+    fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.plan);
     delete &w;
     e.bh = nullptr;
 }

@@ -251,7 +251,7 @@ int dist_init(Engine& e, int rank, int world, int max_particles) {
     NB_CUDA(cudaMalloc(&e.arena.base, e.lay.bytes));
     NB_CUDA(cudaMemset(e.arena.base, 0, e.lay.bytes));
     if (world > 1) {
-        e.bh_lay.set(L);
+        e.bh_lay.set(L, world, static_cast<size_t>(max_particles));
         NB_CUDA(cudaMalloc(&e.bh_arena, e.bh_lay.bytes));
         NB_CUDA(cudaMemset(e.bh_arena, 0, e.bh_lay.bytes));
     }

@@ -43,23 +43,47 @@ struct ArenaLayout {
     }
 };
 
-// Second symmetric allocation, used by the domain-partitioned Barnes-Hut step (nb_bh.cu): this rank's
-// subtree blocks and cell table (walked in place by the peers over NVLink), the accelerations the peers
-// scatter to this rank's bodies, and two epoch-flag rows (trees ready / walks done).
+// Second symmetric allocation, used by the domain-partitioned Barnes-Hut step (nb_bh.cu).  Everything a PEER touches
+// lives here; offsets are identical on every rank.
+//   flags[4][64]        epoch flags of the step's four cross-rank ordering points (boxes / bodies / trees / walks)
+//   aabb[G][4]          aabb[s] = rank s's local bounding box (ordered-int encoded), written by rank s
+//   count_in[G]         count_in[s] = bodies rank s delivered into inbox region s this step, written by rank s
+//   cellwork[2][cells]  walk cost per cut-level cell measured by this rank's walk (double-buffered by step parity)
+//   celltab[cells]      this rank's entries of the cut-level cell table (read by every rank's top-tree build)
+//   in_key/in_rec[G][R] inbox: region s receives the (key-sorted) bodies rank s owns by index that fall into THIS rank's
+//                       cells -- peer stores over NVLink (the all-to-all-v of the step)
+//   nblk / ncblk        this rank's subtree forest (block-SoA records + child indices), walked in place by the peers
+//   acc[L_cap]          accelerations of the bodies this rank owns by index, scattered here by whoever walked them
+constexpr int kBhCutLevel = 5;
+constexpr int kBhNumCells = 1 << (2 * kBhCutLevel);   // 1024 cells at the cut level
+constexpr int kBhFlagRows = 4;
 struct BhArenaLayout {
+    int world = 1;
+    size_t R = 0;            // inbox region capacity (bodies) per source rank = shard capacity
+    size_t cap_bodies = 0;   // most bodies one part may hold: the whole set (any imbalance is legal, only slow)
     int cap_blocks = 0;
-    size_t off_nblk = 0, off_ncblk = 0, off_celltab = 0, off_acc = 0, off_flags = 0, bytes = 0;
-    void set(size_t shard_len) {
-        size_t cb = 3 * shard_len + 4096;
+    size_t off_flags = 0, off_aabb = 0, off_count_in = 0, off_cellwork = 0, off_celltab = 0, off_in_key = 0, off_in_rec = 0,
+           off_nblk = 0, off_ncblk = 0, off_acc = 0, bytes = 0;
+    void set(size_t shard_cap, int world_, size_t max_particles) {
+        world = world_;
+        R = shard_cap;
+        cap_bodies = max_particles;
+        size_t cb = 2 * max_particles + 4096;
         if (cb > (size_t(1) << 22) - 1) cb = (size_t(1) << 22) - 1;
         cap_blocks = static_cast<int>(cb);
         size_t o = 0;
-        off_nblk = o; o += cb * 64;
-        off_ncblk = o; o += cb * 16;
-        off_celltab = o; o += 1024 * 48;
-        off_acc = o; o += shard_len * 8;
-        off_flags = o; o += 2 * 64 * sizeof(uint32_t);
-        bytes = (o + 255) & ~size_t(255);
+        auto take = [&](size_t bytes_) { size_t at = o; o = (o + bytes_ + 255) & ~size_t(255); return at; };
+        off_flags = take(kBhFlagRows * 64 * sizeof(uint32_t));
+        off_aabb = take(kMaxRanks * 4 * sizeof(int));
+        off_count_in = take(kMaxRanks * sizeof(int));
+        off_cellwork = take(2 * kBhNumCells * sizeof(unsigned));
+        off_celltab = take(kBhNumCells * 64);
+        off_in_key = take(static_cast<size_t>(world) * R * 8);
+        off_in_rec = take(static_cast<size_t>(world) * R * 16);
+        off_nblk = take(cb * 64);
+        off_ncblk = take(cb * 16);
+        off_acc = take(shard_cap * 8);
+        bytes = o;
     }
 };
 
