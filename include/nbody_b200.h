@@ -72,6 +72,23 @@ void nb_set_particles(const float *aos5, int32_t n);
 void nb_get_particles(float *aos5_out, int32_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Prefixed aliases of the eight symbols above -- the same functions under names that cannot collide.
+ * The reference links ONE static archive (Cargo.toml:5-7 crate-type staticlib, rust-exp.cabal:46-47) whose
+ * nbody module must keep exporting nb_*: the replacement module (rust-shim/nbody.rs) defines nb_* as
+ * #[no_mangle] forwarders to these, and libnbody_b200.a is linked into the archive.  In the static library the
+ * unprefixed names live in a separate object (nb_alias.o) that the linker only pulls in when nothing else
+ * defines nb_*, so both integration styles link without duplicate symbols.
+ * ---------------------------------------------------------------------------------------------- */
+int32_t b200_nb_num_particles(void);
+void b200_nb_random_disk(int32_t num_particles);
+void b200_nb_stable_orbits(int32_t num_particles, float rmin, float rmax);
+void b200_nb_step_brute_force(float dt);
+void b200_nb_step_barnes_hut(float theta, float dt, int32_t nthreads);
+void b200_nb_draw(int32_t w, int32_t h, uint32_t *fb);
+void b200_nb_set_particles(const float *aos5, int32_t n);
+void b200_nb_get_particles(float *aos5_out, int32_t n);
+
+/* ------------------------------------------------------------------------------------------------
  * Extension surface.
  * ---------------------------------------------------------------------------------------------- */
 

@@ -26,6 +26,15 @@ SYMBOLS = {
     # required additions
     "nb_set_particles": (None, [vp, i32]),
     "nb_get_particles": (None, [vp, i32]),
+    # prefixed aliases (the Rust shim of INTEGRATION.md option A forwards to these)
+    "b200_nb_num_particles": (i32, []),
+    "b200_nb_random_disk": (None, [i32]),
+    "b200_nb_stable_orbits": (None, [i32, f32, f32]),
+    "b200_nb_step_brute_force": (None, [f32]),
+    "b200_nb_step_barnes_hut": (None, [f32, f32, i32]),
+    "b200_nb_draw": (None, [i32, i32, vp]),
+    "b200_nb_set_particles": (None, [vp, i32]),
+    "b200_nb_get_particles": (None, [vp, i32]),
     # extension surface
     "nbx_init": (i32, [i32]),
     "nbx_shutdown": (None, []),

@@ -1,4 +1,9 @@
-// nb_abi.cu -- the extern "C" surface of libnbody_b200.so (include/nbody_b200.h).
+// nb_abi.cu -- the extern "C" surface of libnbody_b200 (include/nbody_b200.h).
+//
+// The implementations carry the b200_ prefix; nb_alias.cu adds the unprefixed nb_* names as one-line forwarders in a
+// SEPARATE object, so that a host module which itself defines nb_* (the Rust shim that replaces rs-src/nbody.rs inside
+// the rust_exp static archive) can link libnbody_b200.a without duplicate symbols -- the linker then never pulls
+// nb_alias.o out of the archive.
 //
 // The six reference symbols keep the exact names / argument order / C types that
 // hs-src/RustNBodyExperiment.hs:101-106 imports from rs-src/nbody.rs; each takes the engine mutex for
@@ -30,13 +35,13 @@ static void replace_set_end(Engine& e) {
 extern "C" {
 
 // rs-src/nbody.rs:34-37
-int32_t nb_num_particles(void) {
+int32_t b200_nb_num_particles(void) {
     NB_LOCK();
     return engine().n;
 }
 
 // rs-src/nbody.rs:39-64
-void nb_random_disk(int32_t num_particles) {
+void b200_nb_random_disk(int32_t num_particles) {
     NB_LOCK();
     Engine& e = engine();
     replace_set_begin(e, num_particles);
@@ -45,7 +50,7 @@ void nb_random_disk(int32_t num_particles) {
 }
 
 // rs-src/nbody.rs:73-104
-void nb_stable_orbits(int32_t num_particles, float rmin, float rmax) {
+void b200_nb_stable_orbits(int32_t num_particles, float rmin, float rmax) {
     NB_LOCK();
     Engine& e = engine();
     // the reference always pushes the sun, then num_particles-1 planets (rs-src/nbody.rs:93-95)
@@ -65,7 +70,7 @@ static bool sync_steps() {
 }
 
 // rs-src/nbody.rs:106-162
-void nb_step_brute_force(float dt) {
+void b200_nb_step_brute_force(float dt) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
@@ -74,7 +79,7 @@ void nb_step_brute_force(float dt) {
 }
 
 // rs-src/nbody.rs:186-480 -- theta first
-void nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
+void b200_nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
@@ -90,7 +95,7 @@ void nb_step_barnes_hut(float theta, float dt, int32_t nthreads) {
 }
 
 // rs-src/nbody.rs:482-583
-void nb_draw(int32_t w, int32_t h, uint32_t* fb) {
+void b200_nb_draw(int32_t w, int32_t h, uint32_t* fb) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
@@ -98,7 +103,7 @@ void nb_draw(int32_t w, int32_t h, uint32_t* fb) {
 }
 
 // ---- required additions ---------------------------------------------------------------------------
-void nb_set_particles(const float* aos5, int32_t n) {
+void b200_nb_set_particles(const float* aos5, int32_t n) {
     NB_LOCK();
     Engine& e = engine();
     replace_set_begin(e, n);
@@ -106,7 +111,7 @@ void nb_set_particles(const float* aos5, int32_t n) {
     replace_set_end(e);
 }
 
-void nb_get_particles(float* aos5_out, int32_t n) {
+void b200_nb_get_particles(float* aos5_out, int32_t n) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);

@@ -17,7 +17,7 @@ def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"typedef struct.*?\}\s*\w+;", "", src, flags=re.S)
-    names = re.findall(r"\b(nbx?3?_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b((?:b200_)?nbx?3?_[a-z0-9_]+)\s*\(", src)
     return sorted(set(names))
 
 
@@ -30,6 +30,8 @@ def test_reference_surface_is_exactly_the_six_symbols_plus_two():
     assert ref == sorted([
         "nb_num_particles", "nb_random_disk", "nb_stable_orbits", "nb_step_brute_force",
         "nb_step_barnes_hut", "nb_draw", "nb_set_particles", "nb_get_particles"])
+    # ...each with a b200_-prefixed alias (for hosts that define nb_* themselves, INTEGRATION.md option A)
+    assert sorted(n for n in header_functions() if n.startswith("b200_")) == sorted("b200_" + n for n in ref)
 
 
 def test_library_exports_every_declared_symbol():

@@ -241,7 +241,12 @@ def test_c5_size_4m_theta075_vs_oracle(fresh, oracle, gen):
         assert abs(c["bh_nodes_visited"] - vis) <= 2e-4 * vis
         assert 0.05 < c["bh_pop_lanes"] / (32.0 * c["bh_pops"]) <= 1.0     # lane-efficiency counters are live
         rel = np.sqrt(((a - f) ** 2).sum(1)) / fn
-        assert np.median(rel) <= 1e-4 and np.quantile(rel, 0.999) <= 1e-3 and rel.max() <= 5e-2
+        # disk (unequal masses): the reference's f32 tree sums sit ~3e-5 from the f64-summed ones.  Plummer (4M EQUAL
+        # masses of 0.01): its f32 running sums stall -- 41,943 + 0.01 rounds in steps of 0.0039 -- and its forces are
+        # ~4e-3 from the f64 brute force (measured, profiles/r02_c5_parity_probe.jsonl), FAST ~1.2e-3: the distance
+        # between the two is the reference's own error, and check (3) below is what holds FAST to the truth.
+        med, q999, mx = (1e-4, 1e-3, 5e-2) if gen == "disk" else (5e-3, 3e-2, 1e-1)
+        assert np.median(rel) <= med and np.quantile(rel, 0.999) <= q999 and rel.max() <= mx
         e_gpu = (np.sqrt(((a[rows] - a64) ** 2).sum(1)) / np.sqrt((a64 ** 2).sum(1))).mean()
         e_ref = (np.sqrt(((f[rows] - a64) ** 2).sum(1)) / np.sqrt((a64 ** 2).sum(1))).mean()
         assert e_gpu <= 1.02 * e_ref
@@ -252,7 +257,7 @@ def test_c5_size_4m_theta075_vs_oracle(fresh, oracle, gen):
             g, r = fresh.get_particles(), ref_step[dt]
             ep = np.abs(g[:, :2].astype(np.float64) - r[:, :2]).max(1) / np.abs(r[:, :2]).max()
             ev = np.abs(g[:, 2:4].astype(np.float64) - r[:, 2:4]).max(1) / np.abs(r[:, 2:4]).max()
-            if dt == 0.001:
+            if dt == 0.001 or gen == "plummer":
                 assert ep.max() <= 1e-4 and np.quantile(ev, 0.999) <= 1e-3
             else:
                 assert (ep <= 1e-4).mean() >= 0.9 and np.quantile(ep, 0.999) <= 1e-3 and np.quantile(ev, 0.999) <= 1e-3
