@@ -302,38 +302,45 @@ __global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float
 // the tile sums sequentially, then a fixed in-tile scan.  blockIdx.y selects one of the 3 arrays.
 constexpr int kScanThreads = 256, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
 
-// len = len_arg, or *len_dev + len_add when the length only exists on the device (partitioned step); the grid is then
-// sized for the capacity and tiles beyond the length contribute zeros.
+// len = len_arg, or *len_dev + len_add when the length only exists on the device (partitioned step): blocks stride
+// over the tiles the actual length needs, so a grid sized for the capacity costs nothing.
 template <typename T>
 __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const T* __restrict__ in, int len_arg, const int* __restrict__ len_dev,
                                                                       int len_add, size_t stride, T* __restrict__ tile_sums, int ntiles) {
     using BR = cub::BlockReduce<T, kScanThreads>;
     __shared__ typename BR::TempStorage tmp;
     const int len = len_dev ? *len_dev + len_add : len_arg;
+    const int nt = min(ntiles, (len + kScanTile - 1) / kScanTile);
     const T* a = in + blockIdx.y * stride;
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    T v = T(0);
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        const int base = tile * kScanTile + threadIdx.x * kScanItems;
+        T v = T(0);
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) v += (base + k < len) ? a[base + k] : T(0);
-    const T t = BR(tmp).Sum(v);
-    if (threadIdx.x == 0) tile_sums[blockIdx.y * ntiles + blockIdx.x] = t;
+        for (int k = 0; k < kScanItems; k++) v += (base + k < len) ? a[base + k] : T(0);
+        const T t = BR(tmp).Sum(v);
+        if (threadIdx.x == 0) tile_sums[blockIdx.y * ntiles + tile] = t;
+        __syncthreads();
+    }
 }
 template <typename T>
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(T* tile_sums, int ntiles) {
+__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets_kernel(T* tile_sums, int ntiles, int len_arg, const int* __restrict__ len_dev,
+                                                                         int len_add) {
     // one block per array: chunks of kScanThreads tiles, fixed block-scan tree + a sequential carry
     using BS = cub::BlockScan<T, kScanThreads>;
     __shared__ typename BS::TempStorage tmp;
     __shared__ T carry;
+    const int len = len_dev ? *len_dev + len_add : len_arg;
+    const int nt = min(ntiles, (len + kScanTile - 1) / kScanTile);
     T* t = tile_sums + blockIdx.x * ntiles;
     if (threadIdx.x == 0) carry = T(0);
     __syncthreads();
-    for (int base = 0; base < ntiles; base += kScanThreads) {
+    for (int base = 0; base < nt; base += kScanThreads) {
         const int i = base + threadIdx.x;
-        const T v = i < ntiles ? t[i] : T(0);
+        const T v = i < nt ? t[i] : T(0);
         T ex, total;
         BS(tmp).ExclusiveSum(v, ex, total);
         const T c = carry;
-        if (i < ntiles) t[i] = c + ex;
+        if (i < nt) t[i] = c + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry = c + total;
         __syncthreads();
@@ -346,26 +353,31 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const T* __res
     using BS = cub::BlockScan<T, kScanThreads>;
     __shared__ typename BS::TempStorage tmp;
     const int len = len_dev ? *len_dev + len_add : len_arg;
-    if (blockIdx.x * kScanTile >= len) return;
+    const int nt = min(ntiles, (len + kScanTile - 1) / kScanTile);
     const T* a = in + blockIdx.y * stride;
     T* o = out + blockIdx.y * stride;
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    T v[kScanItems];
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        const int base = tile * kScanTile + threadIdx.x * kScanItems;
+        T v[kScanItems];
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) v[k] = (base + k < len) ? a[base + k] : T(0);
-    BS(tmp).ExclusiveSum(v, v);
-    const T off = tile_offs[blockIdx.y * ntiles + blockIdx.x];
+        for (int k = 0; k < kScanItems; k++) v[k] = (base + k < len) ? a[base + k] : T(0);
+        BS(tmp).ExclusiveSum(v, v);
+        const T off = tile_offs[blockIdx.y * ntiles + tile];
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) if (base + k < len) o[base + k] = off + v[k];
+        for (int k = 0; k < kScanItems; k++) if (base + k < len) o[base + k] = off + v[k];
+        __syncthreads();
+    }
 }
 
 // exclusive scan of `arrays` arrays of `len` items each (plane stride `stride`), fixed association => deterministic
 template <typename T>
-static void launch_scan(cudaStream_t s, const T* in, T* out, T* tile_sums, int arrays, int len_cap, const int* len_dev, int len_add, size_t stride) {
+static void launch_scan(cudaStream_t s, const T* in, T* out, T* tile_sums, int arrays, int len_cap, const int* len_dev, int len_add,
+                        size_t stride, int max_blocks) {
     const int ntiles = (len_cap + kScanTile - 1) / kScanTile;
-    scan_tile_sums_kernel<T><<<dim3(ntiles, arrays), kScanThreads, 0, s>>>(in, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
-    scan_tile_offsets_kernel<T><<<arrays, kScanThreads, 0, s>>>(tile_sums, ntiles);
-    scan_apply_kernel<T><<<dim3(ntiles, arrays), kScanThreads, 0, s>>>(in, out, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
+    const int gx = std::max(1, std::min(ntiles, max_blocks));
+    scan_tile_sums_kernel<T><<<dim3(gx, arrays), kScanThreads, 0, s>>>(in, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
+    scan_tile_offsets_kernel<T><<<arrays, kScanThreads, 0, s>>>(tile_sums, ntiles, len_cap, len_dev, len_add);
+    scan_apply_kernel<T><<<dim3(gx, arrays), kScanThreads, 0, s>>>(in, out, len_cap, len_dev, len_add, stride, tile_sums, ntiles);
 }
 
 // ---- build: single pass over the sorted keys, no level synchronisation ---------------------------------
@@ -1086,7 +1098,7 @@ static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, 
         PhaseScope ps(e, 6);
         bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
         e.ctr.kernel_launches++;
-        launch_scan<double>(s, w.w3, w.p3, w.tile_sums, 3, n + 1, nullptr, 0, stride);
+        launch_scan<double>(s, w.w3, w.p3, w.tile_sums, 3, n + 1, nullptr, 0, stride, 1 << 30);
         e.ctr.kernel_launches += 3;
     }
     {
@@ -1275,6 +1287,17 @@ __global__ void bhp_wait_kernel(const char* arena, size_t off_flags, int row, in
     const int g = threadIdx.x;
     if (g < world)
         wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + row * 64 + g, epoch, timeout_ns, g, "Barnes-Hut epoch");
+}
+
+// signal + wait in one launch: thread g tells peer g "I reached `row` of this epoch", then waits for peer g's
+__global__ void bhp_sync_kernel(PeerArenas peers, const char* arena, size_t off_flags, int row, int world, int me, uint32_t epoch,
+                                unsigned long long timeout_ns) {
+    const int g = threadIdx.x;
+    if (g < world) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t*>(peers.a[g] + off_flags + (static_cast<size_t>(row) * 64 + me) * sizeof(uint32_t)) = epoch;
+        wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + row * 64 + g, epoch, timeout_ns, g, "Barnes-Hut epoch");
+    }
 }
 
 // my local box -> slot `me` of every peer's box table, then the "boxes" flag
@@ -1672,6 +1695,17 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     auto src_x = [&](int r) { return e.arena.x(e.lay, e.cur) + (real ? 0 : src_begin(r)); };
     auto src_y = [&](int r) { return e.arena.y(e.lay, e.cur) + (real ? 0 : src_begin(r)); };
     auto src_m = [&](int r) { return e.arena.m(e.lay) + (real ? 0 : src_begin(r)); };
+    // a cross-rank ordering point: real ranks signal + wait in one launch; virtual ranks (one stream) signal all, then wait
+    auto sync_point = [&](int row) {
+        if (real) {
+            bhp_sync_kernel<<<1, 32, 0, s>>>(peers, w.parts[0].arena, lay.off_flags, row, nparts, e.rank, epoch, e.peer_timeout_ns);
+            e.ctr.kernel_launches++;
+        } else {
+            for (int r = 0; r < nlocal; r++) bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, row, nparts, r, epoch);
+            for (int r = 0; r < nlocal; r++) bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, row, nparts, epoch, e.peer_timeout_ns);
+            e.ctr.kernel_launches += 2 * nlocal;
+        }
+    };
     // ---- boxes ------------------------------------------------------------------------------------------------------
     {
         PhaseScope ps(e, 2);
@@ -1723,13 +1757,9 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             SendArgs sa{P.keys_sorted, P.idx_sorted, src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan, nparts, part_id(r), peers,
                         lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R};
             bhp_send_kernel<<<std::max(1, std::min((nl + T - 1) / T, e.num_sms * 8)), T, 0, s>>>(sa);
-            bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagBodies, nparts, part_id(r), epoch);
-            e.ctr.kernel_launches += 2;
-        }
-        for (int r = 0; r < nlocal; r++) {
-            bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagBodies, nparts, epoch, e.peer_timeout_ns);
             e.ctr.kernel_launches++;
         }
+        sync_point(kFlagBodies);
     }
     const int est = static_cast<int>(std::min<size_t>(real ? static_cast<size_t>(e.max_particles) : static_cast<size_t>(n),
                                                       2 * ((static_cast<size_t>(n) + nparts - 1) / nparts) + 4096));   // grid sizing only
@@ -1741,7 +1771,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             const size_t stride = P.cap + 1;
             MergeArgs ma{P.arena, lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R, nparts, P.mkeys, P.sx, P.sy, P.sm, P.gidx, P.w3, stride, P.status};
             bhp_merge_kernel<<<GE, T, 0, s>>>(ma);
-            launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride);
+            launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride, e.num_sms * 4);
             e.ctr.kernel_launches += 4;
         }
     }
@@ -1753,7 +1783,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             const int* nd = &P.status->n_part;
             bh_delta_kernel<<<GE, T, 0, s>>>(P.mkeys, P.sx, P.sy, 0, nd, P.delta, P.close);
             bh_cap_kernel<<<GE, T, 0, s>>>(P.delta, P.close, 0, nd, P.dcap, P.count);
-            launch_scan<int>(s, P.count, P.base, P.itile, 1, static_cast<int>(P.cap), nd, 0, 0);
+            launch_scan<int>(s, P.count, P.base, P.itile, 1, static_cast<int>(P.cap), nd, 0, 0, e.num_sms * 4);
             BuildArgs ba{P.mkeys, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, reinterpret_cast<float4*>(P.arena + lay.off_nblk),
                          reinterpret_cast<int4*>(P.arena + lay.off_ncblk), 0, P.cap_blocks - 2,
                          static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, 1, nd, P.cap + 1};
@@ -1765,8 +1795,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     }
     {
         PhaseScope ps(e, 7);
-        for (int r = 0; r < nlocal; r++) { bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagTrees, nparts, part_id(r), epoch); e.ctr.kernel_launches++; }
-        for (int r = 0; r < nlocal; r++) { bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagTrees, nparts, epoch, e.peer_timeout_ns); e.ctr.kernel_launches++; }
+        sync_point(kFlagTrees);
     }
     // ---- top tree (+ the next partition), then the walk ------------------------------------------------------------------
     TreeTable tt{};
@@ -1804,8 +1833,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PhaseScope ps(e, 7);
         // accelerations were stored to their index owners (over NVLink): publish "my walk is done" and wait until every
         // rank's is (=> my acc buffer is complete, nobody reads my subtrees any more, the inboxes may be overwritten)
-        for (int r = 0; r < nlocal; r++) { bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, kFlagWalks, nparts, part_id(r), epoch); e.ctr.kernel_launches++; }
-        for (int r = 0; r < nlocal; r++) { bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, kFlagWalks, nparts, epoch, e.peer_timeout_ns); e.ctr.kernel_launches++; }
+        sync_point(kFlagWalks);
     }
     PartStatusPtrs sp{};
     for (int r = 0; r < nlocal; r++) sp.p[r] = w.parts[r].status;
