@@ -22,6 +22,7 @@ static void replace_set_begin(Engine& e, int n) {
     if (n < 0) n = 0;
     if (e.dist && e.world > 1) dist_wait_all(e, e.step_count);  // peers may still be reading our arena
     e.n = n;
+    e.set_gen++;
     e.mirror_mass_valid = false;
     ensure_capacity(e, n);
 }

@@ -52,6 +52,8 @@ struct BhStatus {
     int aabb_enc[4];          // ordered-int encodings of x1,y1 (min) and x2,y2 (max)
     int n_mine;
     int n_part;               // partitioned step: bodies this part received (device-side size of its arrays)
+    unsigned delta_hist[kLevels + 1];   // delta_hist[d] = sorted neighbours sharing exactly d key levels (sizes the next sort)
+    int sort_long_run;        // longest run the sort fix-up had to order (> 4096 only)
     int n_interior;
     int n_deep;               // partitioned build: interior nodes at or below the cut level
     int n_top;                // partitioned build: interior nodes of the shared top tree
@@ -95,7 +97,8 @@ struct PartBufs {
     // source side: this part's index shard, keyed and sorted locally
     int src_cap = 0;
     unsigned long long *keys = nullptr, *keys_sorted = nullptr;
-    int *idx = nullptr, *idx_sorted = nullptr;
+    unsigned *k32 = nullptr, *k32_sorted = nullptr;
+    int *idx = nullptr, *idx_sorted = nullptr, *idx_fixed = nullptr;
     // "arena" (peer-visible): real ranks -> pointers into the IPC arena; virtual ranks -> one cudaMalloc with the same layout
     char* arena = nullptr;
     bool arena_owned = false;
@@ -141,6 +144,7 @@ struct BhWork {
     int cap_n = 0;
     unsigned long long *keys = nullptr, *keys_sorted = nullptr;
     int *idx = nullptr, *idx_sorted = nullptr, *mine = nullptr;
+    const int* order = nullptr;   // final sorted order of the last single-tree build (idx_sorted, or idx_l after a partial sort)
     float *sx = nullptr, *sy = nullptr, *sm = nullptr;
     double *w3 = nullptr;      // [3][n+1] weights then prefix sums (m, m*x, m*y)
     double *p3 = nullptr;
@@ -162,12 +166,23 @@ struct BhWork {
     unsigned long long* lk_tmp = nullptr;
     NodeInfo* info = nullptr;
     BhStatus* status = nullptr;
-    BhStatus* status_host = nullptr;
+    // Two pinned status slots (slot = position-buffer parity at the start of the step): a step's status block is copied
+    // behind it and read when the slot comes round again, so the host runs up to two steps ahead of the GPU.
+    struct StatusSlot {
+        BhStatus* host = nullptr;
+        cudaEvent_t ev = nullptr;
+        bool pending = false;
+        bool partitioned = false;
+        int n = 0;
+    } slot[2];
+    int cur_slot = 0;                // slot of the step being enqueued / most recently enqueued
+    BhStatus* status_host = nullptr; // == slot[cur_slot].host
+    int last_nparts_hint = 1;        // parts the last partitioned step split into (per-part body count for the sort sizing)
+    int sort_levels = kLevels;       // key levels the next sort orders on (from the delta histogram of earlier steps)
+    uint64_t seen_set_gen = ~0ull;   // a replaced particle set resets sort_levels: no history to trust
     float2* acc = nullptr;     // per local body: acceleration (FAST) or force (EXACT)
     int cap_acc = 0;
     bool warned = false;
-    bool status_pending = false;
-    cudaEvent_t status_ev = nullptr;
     // CUDA graph of the single-GPU FAST step (one per position-buffer parity): ~20 short launches replayed as one
     struct GraphSlot {
         cudaGraphExec_t exec = nullptr;
@@ -178,6 +193,7 @@ struct BhWork {
         const char* arena = nullptr;
         uint64_t alloc_gen = 0;
         size_t L = 0;
+        int sort_levels = 0;
     } graph[2];
     uint64_t alloc_gen = 0;          // bumped whenever a buffer a captured graph points at is (re)allocated
     bool capturing = false;
@@ -217,6 +233,8 @@ __global__ void bh_reset_kernel(BhStatus* st) {
         st->visited = 0;
         st->n_deep = 0;
         st->n_top = 0;
+        for (int d = 0; d <= kLevels; d++) st->delta_hist[d] = 0u;
+        st->sort_long_run = 0;
         for (int g = 0; g <= kMaxRanks; g++) st->tickets[g] = 0;
         st->pops = 0;
         st->pop_lanes = 0;
@@ -256,7 +274,7 @@ __global__ void bh_aabb_kernel(const float* __restrict__ x, const float* __restr
 
 // ---- keys: the reference's midpoint recursion, kLevels deep ------------------------------------------
 __global__ void bh_keys_kernel(const float* __restrict__ x, const float* __restrict__ y, int n, const BhStatus* st,
-                               unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+                               unsigned long long* __restrict__ keys, int* __restrict__ idx, unsigned* __restrict__ k32 = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x1 = ord2f(st->aabb_enc[0]), y1 = ord2f(st->aabb_enc[1]);
@@ -276,12 +294,90 @@ __global__ void bh_keys_kernel(const float* __restrict__ x, const float* __restr
     }
     keys[i] = key;
     idx[i] = i;
+    if (k32) k32[i] = static_cast<unsigned>(key >> (kKeyBits - 32));   // the top 16 levels
+}
+
+// ---- sort: only the key levels the tree needs ------------------------------------------------------------------------
+// The tree of a set whose deepest split is at level D only needs the bodies ordered by the top D+1 key levels; bodies
+// move less than a cell per step, so last step's depth (+ margin) tells how many levels to sort on: 3-4 radix passes
+// over 32-bit keys instead of 6 over 64-bit ones.  Correctness never depends on the guess: bh_sort_fixup_kernel
+// completes the order inside every run of bodies that share the sorted prefix (normally none or pairs).
+struct SortBufs {
+    unsigned long long *keys, *keys_sorted;   // full 48-bit keys (unsorted) / CUB output of the 64-bit path
+    unsigned *k32, *k32_sorted;               // top 32 bits
+    int *idx, *idx_sorted, *idx_fixed;        // identity, CUB output, final order
+};
+
+// prefix (the sorted-on levels) of sorted position i
+struct SortedPrefix {
+    const unsigned long long* k64;
+    const unsigned* k32;
+    int shift;
+    __device__ __forceinline__ unsigned long long operator()(int i) const {
+        return k32 ? static_cast<unsigned long long>(k32[i] >> shift) : (k64[i] >> shift);
+    }
+};
+
+// every body finds its final position inside its run of equal prefixes: rank by (full key, sorted position) -- stable
+__global__ void bh_sort_fixup_kernel(SortedPrefix pre, const unsigned long long* __restrict__ keys, const int* __restrict__ idx_sorted, int n,
+                                     int* __restrict__ idx_fixed, BhStatus* st) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long p = pre(i);
+        const bool same_l = i > 0 && pre(i - 1) == p, same_r = i + 1 < n && pre(i + 1) == p;
+        const int me = idx_sorted[i];
+        if (!same_l && !same_r) { idx_fixed[i] = me; continue; }
+        int lo = i, hi = i + 1;   // run [lo, hi): galloping + bisection on the sorted prefixes
+        if (same_l) {
+            int step = 1, l = i - 1;
+            while (l - step >= 0 && pre(l - step) == p) { l -= step; step <<= 1; }
+            int a = max(l - step, -1), b = l;          // pre(a) != p (or a == -1), pre(b) == p
+            while (b - a > 1) { const int mid = (a + b) >> 1; if (pre(mid) == p) b = mid; else a = mid; }
+            lo = b;
+        }
+        if (same_r) {
+            int step = 1, r = i + 1;
+            while (r + step < n && pre(r + step) == p) { r += step; step <<= 1; }
+            int a = r, b = min(r + step, n);            // pre(a) == p, pre(b) != p (or b == n)
+            while (b - a > 1) { const int mid = (a + b) >> 1; if (pre(mid) == p) a = mid; else b = mid; }
+            hi = a + 1;
+        }
+        const unsigned long long k = keys[me];
+        int rank = 0;
+        for (int j = lo; j < hi; j++) {
+            const unsigned long long kj = keys[idx_sorted[j]];
+            rank += (kj < k || (kj == k && j < i)) ? 1 : 0;
+        }
+        idx_fixed[lo + rank] = me;
+        if (i == lo && hi - lo > 4096) atomicMax(&st->sort_long_run, hi - lo);   // the depth guess was far off: tell the host
+    }
+}
+
+// sorts (key, index) on the top `levels` key levels and returns the array holding the final order
+static const int* sort_bodies(Engine& e, BhWork& w, const SortBufs& b, int n, int levels, BhStatus* st) {
+    cudaStream_t s = e.stream;
+    size_t tb = w.cub_bytes;
+    if (levels >= kLevels) {
+        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, b.keys, b.keys_sorted, b.idx, b.idx_sorted, n, 0, kKeyBits, s);
+        return b.idx_sorted;
+    }
+    SortedPrefix pre{};
+    if (levels <= 16) {
+        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, b.k32, b.k32_sorted, b.idx, b.idx_sorted, n, 32 - 2 * levels, 32, s);
+        pre.k32 = b.k32_sorted; pre.shift = 32 - 2 * levels;
+    } else {
+        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, b.keys, b.keys_sorted, b.idx, b.idx_sorted, n, kKeyBits - 2 * levels, kKeyBits, s);
+        pre.k64 = b.keys_sorted; pre.shift = kKeyBits - 2 * levels;
+    }
+    bh_sort_fixup_kernel<<<std::max(1, std::min((n + 255) / 256, e.num_sms * 16)), 256, 0, s>>>(pre, b.keys, b.idx_sorted, n, b.idx_fixed, st);
+    e.ctr.kernel_launches++;
+    return b.idx_fixed;
 }
 
 __global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                         const float* __restrict__ m, const int* __restrict__ idx_sorted, int n,
                                         float* __restrict__ sx, float* __restrict__ sy, float* __restrict__ sm,
-                                        double* __restrict__ w3) {
+                                        double* __restrict__ w3, const unsigned long long* __restrict__ keys = nullptr,
+                                        unsigned long long* __restrict__ keys_sorted = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     double wm = 0.0, wx = 0.0, wy = 0.0;
@@ -289,6 +385,7 @@ __global__ void bh_gather_sorted_kernel(const float* __restrict__ x, const float
         const int j = idx_sorted[i];
         const float xx = x[j], yy = y[j], mm = m[j];
         sx[i] = xx; sy[i] = yy; sm[i] = mm;
+        if (keys) keys_sorted[i] = keys[j];   // partial sort: the full keys in final order
         wm = mm; wx = static_cast<double>(mm) * xx; wy = static_cast<double>(mm) * yy;
     }
     const size_t stride = static_cast<size_t>(n) + 1;
@@ -416,9 +513,13 @@ __device__ __forceinline__ void add_mass_ref(float& px, float& py, float& m, flo
 }
 
 // delta[i] for the pair (i, i+1), i in [0, n-1); delta[n-1] = sentinel -1.  n = *n_dev when given (partitioned step).
+// Also histograms delta into st->delta_hist (block-aggregated): the host sizes the next step's sort from it.
 __global__ void bh_delta_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ sx,
                                 const float* __restrict__ sy, int n_arg, const int* __restrict__ n_dev, signed char* __restrict__ delta,
-                                unsigned char* __restrict__ close) {
+                                unsigned char* __restrict__ close, BhStatus* st) {
+    __shared__ unsigned hist[kLevels + 1];
+    if (threadIdx.x <= kLevels) hist[threadIdx.x] = 0u;
+    __syncthreads();
     const int n = n_dev ? *n_dev : n_arg;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (i == n - 1) { delta[i] = -1; close[i] = 0; continue; }
@@ -426,7 +527,12 @@ __global__ void bh_delta_kernel(const unsigned long long* __restrict__ keys, con
         const int d = x ? (__clzll(static_cast<long long>(x)) - (64 - kKeyBits)) >> 1 : kLevels;
         delta[i] = static_cast<signed char>(d);
         close[i] = (fabsf(sx[i] - sx[i + 1]) < kEps && fabsf(sy[i] - sy[i + 1]) < kEps) ? 1 : 0;
+        // warp-aggregated: neighbours in Morton order mostly share the same delta
+        const unsigned peers = __match_any_sync(__activemask(), d);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[d], static_cast<unsigned>(__popc(peers)));
     }
+    __syncthreads();
+    if (threadIdx.x <= kLevels && hist[threadIdx.x]) atomicAdd(&st->delta_hist[threadIdx.x], hist[threadIdx.x]);
 }
 
 __global__ void bh_cap_kernel(const signed char* __restrict__ delta, const unsigned char* __restrict__ close, int n_arg,
@@ -977,6 +1083,8 @@ struct InRange {
 using Iota = thrust::counting_iterator<int>;
 
 static void check_status(Engine& e, struct BhWork& w, bool sync_now);
+static void status_begin(Engine& e, struct BhWork& w);
+static void status_commit(Engine& e, struct BhWork& w, bool partitioned);
 static void bh_forces_partitioned(Engine& e, float theta, int nparts);
 
 // How many domain parts the FAST Barnes-Hut step uses: the world size when sharded over real GPUs (and the
@@ -1061,9 +1169,12 @@ static void ensure_work(Engine& e, BhWork& w, int n) {
 static void ensure_status(BhWork& w) {
     if (!w.status) {
         NB_CUDA(cudaMalloc(&w.status, sizeof(BhStatus)));
-        NB_CUDA(cudaMallocHost(&w.status_host, sizeof(BhStatus)));
-        memset(w.status_host, 0, sizeof(BhStatus));
-        NB_CUDA(cudaEventCreateWithFlags(&w.status_ev, cudaEventDisableTiming));
+        for (auto& sl : w.slot) {
+            NB_CUDA(cudaMallocHost(&sl.host, sizeof(BhStatus)));
+            memset(sl.host, 0, sizeof(BhStatus));
+            NB_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+        }
+        w.status_host = w.slot[0].host;
         NB_CUDA(cudaMalloc(&w.xflags, 4 * sizeof(int)));
         NB_CUDA(cudaMallocHost(&w.xflags_host, 4 * sizeof(int)));
     }
@@ -1083,27 +1194,30 @@ static GlobalPos global_positions(Engine& e) {
 static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, NodeInfo* info) {
     cudaStream_t s = e.stream;
     const int T = 256, G = (n + T - 1) / T;
+    // EXACT (info != nullptr) keeps the full sort: its per-level index sorts below rely on w.idx staying the identity
+    const int levels = info ? kLevels : w.sort_levels;
     {
         PhaseScope ps(e, 3);
-        bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx);
+        bh_keys_kernel<<<G, T, 0, s>>>(gp.x, gp.y, n, w.status, w.keys, w.idx, levels <= 16 ? w.xk : nullptr);
         e.ctr.kernel_launches++;
     }
     {
         PhaseScope ps(e, 4);
-        size_t tb = w.cub_bytes;
-        cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.keys, w.keys_sorted, w.idx, w.idx_sorted, n, 0, kKeyBits, s);
+        SortBufs sb{w.keys, w.keys_sorted, w.xk, w.xk_sorted, w.idx, w.idx_sorted, w.idx_l};
+        w.order = sort_bodies(e, w, sb, n, levels, w.status);
     }
     const size_t stride = static_cast<size_t>(n) + 1;
     {
         PhaseScope ps(e, 6);
-        bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.idx_sorted, n, w.sx, w.sy, w.sm, w.w3);
+        bh_gather_sorted_kernel<<<(n + 1 + T - 1) / T, T, 0, s>>>(gp.x, gp.y, gp.m, w.order, n, w.sx, w.sy, w.sm, w.w3,
+                                                                  levels < kLevels ? w.keys : nullptr, w.keys_sorted);
         e.ctr.kernel_launches++;
         launch_scan<double>(s, w.w3, w.p3, w.tile_sums, 3, n + 1, nullptr, 0, stride, 1 << 30);
         e.ctr.kernel_launches += 3;
     }
     {
         PhaseScope ps(e, 5);
-        bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, nullptr, w.delta, w.close);
+        bh_delta_kernel<<<G, T, 0, s>>>(w.keys_sorted, w.sx, w.sy, n, nullptr, w.delta, w.close, w.status);
         bh_cap_kernel<<<G, T, 0, s>>>(w.delta, w.close, n, nullptr, w.dcap, w.count);
         size_t tb = w.cub_bytes;
         cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
@@ -1119,7 +1233,7 @@ static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, 
 static void bh_forces(Engine& e, float theta) {
     BhWork& w = work(e);
     ensure_status(w);
-    check_status(e, w, false);   // previous step's status (its copy has long finished by now)
+    if (!w.capturing) status_begin(e, w);   // claims this step's status slot (its previous user finished two steps ago)
     const int n = e.n;
     ensure_work(e, w, n);
     const int nl = local_count(e), ib = local_begin(e);
@@ -1135,9 +1249,7 @@ static void bh_forces(Engine& e, float theta) {
     const int nparts = bh_partition_count(e);
     if (nparts > 1) {
         bh_forces_partitioned(e, theta, nparts);
-        NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, e.stream));
-        NB_CUDA(cudaEventRecord(w.status_ev, e.stream));
-        w.status_pending = true;
+        status_commit(e, w, true);
         return;
     }
     // sharded: slot index == body index only while every shard but the last is full (L-aligned shards)
@@ -1215,7 +1327,7 @@ static void bh_forces(Engine& e, float theta) {
         int n_list = n;
         if (e.dist && e.world > 1) {
             size_t tb = w.cub_bytes;
-            cub::DeviceSelect::If(w.cub_tmp, tb, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.idx_sorted, ib, ib + nl}, s);
+            cub::DeviceSelect::If(w.cub_tmp, tb, Iota(0), w.mine, &w.status->n_mine, n, InRange{w.order, ib, ib + nl}, s);
             mine = w.mine;
             n_list = nl;
         }
@@ -1228,15 +1340,11 @@ static void bh_forces(Engine& e, float theta) {
             tt.acc[e.rank] = w.acc;
             tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
             w.last_tt = tt; w.last_nparts = 1;
-            launch_traverse(e, tt, w.sx, w.sy, w.idx_sorted, mine, n_list, theta, w.status);
+            launch_traverse(e, tt, w.sx, w.sy, w.order, mine, n_list, theta, w.status);
         }
     }
     NB_CUDA(cudaGetLastError());
-    NB_CUDA(cudaMemcpyAsync(w.status_host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, s));
-    if (!w.capturing) {
-        NB_CUDA(cudaEventRecord(w.status_ev, s));
-        w.status_pending = true;
-    }
+    status_commit(e, w, false);
 }
 
 // =================================================================================================
@@ -1333,8 +1441,8 @@ __global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size
 
 // ---- send: the key-sorted shard -> the inbox regions of the parts that own its cells --------------------------------
 struct SendArgs {
-    const unsigned long long* keys_sorted;
-    const int* idx_sorted;
+    const unsigned long long* keys;   // full keys of the shard (unsorted); the key of sorted position i is keys[order[i]]
+    const int* order;
     const float *x, *y, *m;
     int n_local, gbegin;
     const PartPlan* plan;
@@ -1348,7 +1456,7 @@ __global__ void __launch_bounds__(256) bhp_send_kernel(const SendArgs a) {
         // first sorted body whose cut-level cell is >= cut[p]: the start of part p's run
         const unsigned long long kmin = static_cast<unsigned long long>(a.plan->cut[threadIdx.x]) << kCellShift;
         int l = 0, h = a.n_local;
-        while (l < h) { const int mid = (l + h) >> 1; if (a.keys_sorted[mid] < kmin) l = mid + 1; else h = mid; }
+        while (l < h) { const int mid = (l + h) >> 1; if (a.keys[a.order[mid]] < kmin) l = mid + 1; else h = mid; }
         lo[threadIdx.x] = l;
     }
     __syncthreads();
@@ -1357,9 +1465,9 @@ __global__ void __launch_bounds__(256) bhp_send_kernel(const SendArgs a) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_local; i += gridDim.x * blockDim.x) {
         int p = 0;
         while (p + 1 < a.nparts && i >= lo[p + 1]) p++;
-        const int j = a.idx_sorted[i];
+        const int j = a.order[i];
         const size_t slot = static_cast<size_t>(a.me) * a.R + static_cast<size_t>(i - lo[p]);
-        reinterpret_cast<unsigned long long*>(a.peers.a[p] + a.off_in_key)[slot] = a.keys_sorted[i];
+        reinterpret_cast<unsigned long long*>(a.peers.a[p] + a.off_in_key)[slot] = a.keys[j];
         reinterpret_cast<float4*>(a.peers.a[p] + a.off_in_rec)[slot] = make_float4(a.x[j], a.y[j], a.m[j], __int_as_float(a.gbegin + j));
     }
 }
@@ -1575,10 +1683,14 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
 struct PartStatusPtrs { BhStatus* p[kMaxRanks]; };
 __global__ void bhp_fold_status_kernel(BhStatus* global, PartStatusPtrs parts, int nlocal) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int deep = 0, ovf = 0;
-        for (int r = 0; r < nlocal; r++) { deep += parts.p[r]->n_deep; ovf |= parts.p[r]->overflow; }
+        int deep = 0, ovf = 0, run = 0;
+        for (int r = 0; r < nlocal; r++) {
+            deep += parts.p[r]->n_deep; ovf |= parts.p[r]->overflow; run = max(run, parts.p[r]->sort_long_run);
+            for (int d = 0; d <= kLevels; d++) global->delta_hist[d] += parts.p[r]->delta_hist[d];
+        }
         global->n_deep += deep;
         global->overflow |= ovf;
+        global->sort_long_run = max(global->sort_long_run, run);
     }
 }
 __global__ void bhp_plan_init_kernel(PartPlan* plan2, int nparts) {
@@ -1590,7 +1702,7 @@ __global__ void bhp_plan_init_kernel(PartPlan* plan2, int nparts) {
 // ---- partitioned step: host side -------------------------------------------------------------------------
 static void part_free(PartBufs& P) {
     auto fr = [](void* p) { if (p) cudaFree(p); };
-    fr(P.keys); fr(P.keys_sorted); fr(P.idx); fr(P.idx_sorted);
+    fr(P.keys); fr(P.keys_sorted); fr(P.idx); fr(P.idx_sorted); fr(P.k32); fr(P.k32_sorted); fr(P.idx_fixed);
     fr(P.mkeys); fr(P.sx); fr(P.sy); fr(P.sm); fr(P.gidx); fr(P.w3); fr(P.p3); fr(P.tile_sums);
     fr(P.delta); fr(P.dcap); fr(P.close); fr(P.count); fr(P.base); fr(P.owner); fr(P.itile); fr(P.status);
     if (P.arena_owned) fr(P.arena);
@@ -1605,7 +1717,8 @@ static void part_ensure(Engine& e, BhWork& w, PartBufs& P, int src_cap, size_t c
     part_free(P);
     const size_t S = static_cast<size_t>(src_cap), N = cap;
     NB_CUDA(cudaMalloc(&P.keys, S * 8)); NB_CUDA(cudaMalloc(&P.keys_sorted, S * 8));
-    NB_CUDA(cudaMalloc(&P.idx, S * 4)); NB_CUDA(cudaMalloc(&P.idx_sorted, S * 4));
+    NB_CUDA(cudaMalloc(&P.idx, S * 4)); NB_CUDA(cudaMalloc(&P.idx_sorted, S * 4)); NB_CUDA(cudaMalloc(&P.idx_fixed, S * 4));
+    NB_CUDA(cudaMalloc(&P.k32, S * 4)); NB_CUDA(cudaMalloc(&P.k32_sorted, S * 4));
     NB_CUDA(cudaMalloc(&P.mkeys, N * 8));
     NB_CUDA(cudaMalloc(&P.sx, N * 4)); NB_CUDA(cudaMalloc(&P.sy, N * 4)); NB_CUDA(cudaMalloc(&P.sm, N * 4)); NB_CUDA(cudaMalloc(&P.gidx, N * 4));
     NB_CUDA(cudaMalloc(&P.w3, 3 * (N + 1) * 8)); NB_CUDA(cudaMalloc(&P.p3, 3 * (N + 1) * 8));
@@ -1730,11 +1843,17 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         }
     }
     // ---- keys + sort of the own shard ----------------------------------------------------------------------------------
+    const int levels = w.sort_levels;
+    const int* order[kMaxRanks] = {};
     {
         PhaseScope ps(e, 3);
         for (int r = 0; r < nlocal; r++) {
             const int nl = src_count(r);
-            if (nl > 0) { bh_keys_kernel<<<(nl + T - 1) / T, T, 0, s>>>(src_x(r), src_y(r), nl, w.parts[r].status, w.parts[r].keys, w.parts[r].idx); e.ctr.kernel_launches++; }
+            if (nl > 0) {
+                bh_keys_kernel<<<(nl + T - 1) / T, T, 0, s>>>(src_x(r), src_y(r), nl, w.parts[r].status, w.parts[r].keys, w.parts[r].idx,
+                                                            levels <= 16 ? w.parts[r].k32 : nullptr);
+                e.ctr.kernel_launches++;
+            }
         }
     }
     {
@@ -1742,9 +1861,10 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
             const int nl = src_count(r);
+            order[r] = P.idx_sorted;
             if (nl > 0) {
-                size_t tb = w.cub_bytes;
-                cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, P.keys, P.keys_sorted, P.idx, P.idx_sorted, nl, 0, kKeyBits, s);
+                SortBufs sb{P.keys, P.keys_sorted, P.k32, P.k32_sorted, P.idx, P.idx_sorted, P.idx_fixed};
+                order[r] = sort_bodies(e, w, sb, nl, levels, P.status);
             }
         }
     }
@@ -1754,7 +1874,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
             const int nl = src_count(r);
-            SendArgs sa{P.keys_sorted, P.idx_sorted, src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan, nparts, part_id(r), peers,
+            SendArgs sa{P.keys, order[r], src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan, nparts, part_id(r), peers,
                         lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R};
             bhp_send_kernel<<<std::max(1, std::min((nl + T - 1) / T, e.num_sms * 8)), T, 0, s>>>(sa);
             e.ctr.kernel_launches++;
@@ -1781,7 +1901,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
             const int* nd = &P.status->n_part;
-            bh_delta_kernel<<<GE, T, 0, s>>>(P.mkeys, P.sx, P.sy, 0, nd, P.delta, P.close);
+            bh_delta_kernel<<<GE, T, 0, s>>>(P.mkeys, P.sx, P.sy, 0, nd, P.delta, P.close, P.status);
             bh_cap_kernel<<<GE, T, 0, s>>>(P.delta, P.close, 0, nd, P.dcap, P.count);
             launch_scan<int>(s, P.count, P.base, P.itile, 1, static_cast<int>(P.cap), nd, 0, 0, e.num_sms * 4);
             BuildArgs ba{P.mkeys, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, reinterpret_cast<float4*>(P.arena + lay.off_nblk),
@@ -1841,24 +1961,38 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     e.ctr.kernel_launches++;
     w.acc_src = real ? reinterpret_cast<float2*>(e.bh_arena + lay.off_acc) : w.acc;
     w.last_partitioned = true;
-    w.last_tt = tt; w.last_nparts = nparts;
+    w.last_tt = tt; w.last_nparts = nparts; w.last_nparts_hint = nparts;
     NB_CUDA(cudaGetLastError());
 }
 
-// Deferred: the status block of a step is copied to pinned memory behind the step and looked at when the
-// NEXT Barnes-Hut call (or any synchronising call) arrives, so stepping never stalls the host on the GPU.
-static void check_status(Engine& e, BhWork& w, bool sync_now) {
-    if (!w.status_pending) return;
-    if (sync_now) NB_CUDA(cudaEventSynchronize(w.status_ev));
-    else if (cudaEventQuery(w.status_ev) != cudaSuccess) { (void)cudaGetLastError(); NB_CUDA(cudaEventSynchronize(w.status_ev)); }
-    w.status_pending = false;
-    const BhStatus& h = *w.status_host;
+// Deferred: the status block of a step is copied to pinned memory behind the step and looked at when its slot comes
+// round again (two steps later) or at any synchronising call, so stepping never stalls the host on the GPU.
+static int choose_sort_levels(const BhStatus& h, int n) {
+    if (n < 8192) return kLevels;
+    // sorting on L levels leaves the neighbours that share >= L levels to the fix-up: keep those below n/128
+    unsigned long long tail = 0;
+    int L = 0;
+    for (int d = kLevels; d >= 0; d--) {
+        tail += h.delta_hist[d];
+        if (tail * 128ull > static_cast<unsigned long long>(n)) { L = d + 1; break; }
+    }
+    return std::max(6, std::min(kLevels, L + 1));
+}
+static void process_slot(Engine& e, BhWork& w, int k, bool wait) {
+    BhWork::StatusSlot& sl = w.slot[k];
+    if (!sl.pending) return;
+    if (wait) NB_CUDA(cudaEventSynchronize(sl.ev));
+    else if (cudaEventQuery(sl.ev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+    sl.pending = false;
+    const BhStatus& h = *sl.host;
     if (h.depth_error) fatal("Node::insert() - recursion depth > 50 (the reference panics here, rs-src/nbody.rs:230-232)", __FILE__, __LINE__);
     if (h.overflow && !w.warned) {
         fprintf(stderr, "nbody_b200: warning: quadtree node pool exhausted (%d nodes); deepest cells were merged\n", w.cap_nodes);
         w.warned = true;
     }
-    if (w.last_partitioned)   // this rank's share; rank 0 (or the single process) also counts the shared top tree
+    if (h.sort_long_run > 0)
+        fprintf(stderr, "nbody_b200: note: the partial sort left a run of %d bodies to its fix-up (the set changed abruptly)\n", h.sort_long_run);
+    if (sl.partitioned)   // this rank's share; rank 0 (or the single process) also counts the shared top tree
         e.ctr.bh_nodes_built += 4ull * static_cast<uint64_t>(h.n_deep) + (e.rank == 0 ? 1ull + 4ull * static_cast<uint64_t>(h.n_top) : 0ull);
     else
         e.ctr.bh_nodes_built += static_cast<uint64_t>(h.node_count);
@@ -1866,7 +2000,34 @@ static void check_status(Engine& e, BhWork& w, bool sync_now) {
     e.ctr.bh_nodes_visited += h.visited;
     e.ctr.bh_pops += h.pops;
     e.ctr.bh_pop_lanes += h.pop_lanes;
-    for (int k = 0; k < 33; k++) w.pop_hist[k] += h.pop_hist[k];
+    for (int q = 0; q < 33; q++) w.pop_hist[q] += h.pop_hist[q];
+    if (e.mode == NBX_MODE_FAST && sl.n > 0) w.sort_levels = choose_sort_levels(h, sl.n);
+}
+static void check_status(Engine& e, BhWork& w, bool sync_now) {
+    // older slot first, so that sort_levels ends up from the most recent step
+    const int older = w.cur_slot ^ 1;
+    process_slot(e, w, older, sync_now);
+    process_slot(e, w, w.cur_slot, sync_now);
+}
+// start of a Barnes-Hut call: claim the status slot of this position-buffer parity (wait for its previous user)
+static void status_begin(Engine& e, BhWork& w) {
+    const int k = e.cur & 1;
+    process_slot(e, w, k ^ 1, false);
+    process_slot(e, w, k, true);
+    w.cur_slot = k;
+    w.status_host = w.slot[k].host;
+    if (w.seen_set_gen != e.set_gen) { w.seen_set_gen = e.set_gen; w.sort_levels = kLevels; }
+}
+// end of the device work of a Barnes-Hut call: queue the status copy behind it
+static void status_commit(Engine& e, BhWork& w, bool partitioned) {
+    BhWork::StatusSlot& sl = w.slot[w.cur_slot];
+    NB_CUDA(cudaMemcpyAsync(sl.host, w.status, sizeof(BhStatus), cudaMemcpyDeviceToHost, e.stream));
+    sl.partitioned = partitioned;
+    sl.n = (partitioned && e.dist && e.world > 1) ? e.n / std::max(1, w.last_nparts_hint) : e.n;   // bodies the histogram covers
+    if (!w.capturing) {
+        NB_CUDA(cudaEventRecord(sl.ev, e.stream));
+        sl.pending = true;
+    }
 }
 void bh_pop_histogram(Engine& e, uint64_t* out33, bool reset) {
     for (int k = 0; k < 33; k++) out33[k] = 0;
@@ -1900,7 +2061,7 @@ void bh_step(Engine& e, float theta, float dt) {
     BhWork& w = work(e);
     if (bh_graph_eligible(e)) {
         ensure_status(w);
-        check_status(e, w, false);
+        status_begin(e, w);
         ensure_work(e, w, e.n);
         if (local_count(e) > w.cap_acc) {   // same sizing rule as bh_forces: allocate outside the capture
             NB_CUDA(cudaStreamSynchronize(e.stream));
@@ -1912,7 +2073,7 @@ void bh_step(Engine& e, float theta, float dt) {
         BhWork::GraphSlot& g = w.graph[e.cur];
         // every pointer and scalar a captured launch carries is a function of this key (alloc_gen covers the workspace)
         const bool hit = g.exec && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
-                         g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L;
+                         g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L && g.sort_levels == w.sort_levels;
         if (!hit) {
             // Re-capture (host-only work, ~20 nodes) and patch the instantiated graph in place: a theta / dt change
             // from the reference UI (hs-src/RustNBodyExperiment.hs:88-93) or a reallocation only changes kernel
@@ -1935,7 +2096,7 @@ void bh_step(Engine& e, float theta, float dt) {
             if (!updated) NB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
             NB_CUDA(cudaGraphDestroy(graph));
             g.n = e.n; g.cur = cur0; g.theta = theta; g.dt = dt; g.stream = e.stream; g.arena = e.arena.base;
-            g.alloc_gen = w.alloc_gen; g.L = e.lay.L;
+            g.alloc_gen = w.alloc_gen; g.L = e.lay.L; g.sort_levels = w.sort_levels;
             g.launches = e.ctr.kernel_launches - l0;
             // the capture already advanced the host-side state exactly like a replay does below
         } else {
@@ -1948,8 +2109,9 @@ void bh_step(Engine& e, float theta, float dt) {
             w.last_tt = tt; w.last_nparts = 1;
         }
         NB_CUDA(cudaGraphLaunch(g.exec, e.stream));
-        NB_CUDA(cudaEventRecord(w.status_ev, e.stream));
-        w.status_pending = true;
+        BhWork::StatusSlot& sl = w.slot[w.cur_slot];   // the graph's last node copied the status block into this slot
+        NB_CUDA(cudaEventRecord(sl.ev, e.stream));
+        sl.pending = true; sl.partitioned = false; sl.n = e.n;
     } else {
         bh_step_body(e, w, theta, dt);
     }
@@ -2040,8 +2202,10 @@ void bh_shutdown(Engine& e) {
     auto fr = [](void* p) { if (p) cudaFree(p); };
     fr(w.keys); fr(w.keys_sorted); fr(w.idx); fr(w.idx_sorted); fr(w.mine); fr(w.sx); fr(w.sy); fr(w.sm);
     fr(w.w3); fr(w.p3); fr(w.tile_sums); fr(w.ndata); fr(w.nbounds); fr(w.nchild); fr(w.nblk); fr(w.ncblk); fr(w.delta); fr(w.dcap); fr(w.close); fr(w.count); fr(w.base); fr(w.owner); fr(w.xk); fr(w.xk_sorted); fr(w.xorder); fr(w.idx_l); fr(w.lk_tmp); fr(w.info); fr(w.cub_tmp); fr(w.status); fr(w.acc);
-    if (w.status_host) cudaFreeHost(w.status_host);
-    if (w.status_ev) cudaEventDestroy(w.status_ev);
+    for (auto& sl : w.slot) {
+        if (sl.host) cudaFreeHost(sl.host);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+    }
     for (auto& g : w.graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (PartBufs& P : w.parts) part_free(P);
     fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.plan);

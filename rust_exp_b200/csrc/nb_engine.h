@@ -163,6 +163,7 @@ struct Engine {
     uint64_t peer_timeout_ns = 30000000000ull;   // device-side waits on peers trap after this long (0 = never)
     int cur = 0;                     // current position buffer
     uint32_t step_count = 0;         // steps completed (also the cross-rank flag value)
+    uint64_t set_gen = 0;            // bumped whenever the particle set is replaced (set / generators)
     // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies
     float* mirror = nullptr;
     size_t mirror_cap = 0;
