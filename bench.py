@@ -492,7 +492,13 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
                     "pops_per_step": pops, "lanes_per_pop_histogram": hist,
                     "interactions_per_step": inter, "nodes_visited_per_step": vis, "tree_nodes": nodes,
                     "walk_ms_max_over_ranks": trav_max, "walk_imbalance_max_over_mean": (trav_max / (trav_all / world)) if trav_all > 0 else None,
-                    "theta": w["theta"]})
+                    "theta": w["theta"], "sort_levels": lib.counters()["bh_sort_levels"]})
+        if world > 1:
+            # per-rank view of the partitioned step: bodies in each rank's domain part and its phase times
+            mine = {"rank": rank, "part_bodies": lib.counters()["bh_part_bodies"], **{k: round(v, 4) for k, v in phases.items()}}
+            allr = [None] * world
+            cx.dist.all_gather_object(allr, mine)
+            out["per_rank"] = allr
     out["e2e"] = {"value": e2e_value, "unit": out["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "what": e2e_what}
     if w["kind"] == "bh":

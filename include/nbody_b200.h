@@ -108,6 +108,20 @@ const char *nbx_version(void);
 int32_t nbx_set_mode(int32_t mode);
 int32_t nbx_get_mode(void);
 
+/* Opt-in integrator (the reference author's TODO at rs-src/nbody.rs:449, "Try different integration scheme, Verlet /
+ * RK4 etc.").  EULER (default) is the reference's semi-implicit Euler.  LEAPFROG_KDK is kick-drift-kick leapfrog
+ * (velocity Verlet): v += dt/2 a(x); x += dt v; v += dt/2 a(x') -- second order and time-reversible, one force
+ * evaluation per step (consecutive half kicks are merged) plus one when the state is read back.  It changes results,
+ * so it is never the default; it applies to FAST mode only (EXACT always integrates like the reference). */
+#define NBX_INTEGRATOR_EULER 0
+#define NBX_INTEGRATOR_LEAPFROG_KDK 1
+int32_t nbx_set_integrator(int32_t integrator);
+
+/* Opt-in tree shape (the reference author's TODO at rs-src/nbody.rs:400-407): square up the root box of the quadtree,
+ * exactly as the commented-out code there does (the shorter side is extended from the min corner).  Default 0 = the
+ * reference's tight, non-square box. */
+int32_t nbx_set_square_aabb(int32_t enable);
+
 /* Launch all work on a caller-owned cudaStream_t (e.g. the host framework's current stream) so the
  * caller's CUDA events bracket it.  NULL restores the library's own stream. */
 int32_t nbx_set_stream(void *cuda_stream);
@@ -139,6 +153,10 @@ typedef struct nbx_counters {
      * by all 32 lanes, so bh_pop_lanes / (32 * bh_pops) is the fraction of useful lane work. */
     uint64_t bh_pops;
     uint64_t bh_pop_lanes;
+    /* gauges of the most recent Barnes-Hut step whose status was read back: bodies in this rank's domain part
+     * (partitioned multi-GPU step; n otherwise) and the key levels its sort ordered on */
+    uint64_t bh_part_bodies;
+    uint64_t bh_sort_levels;
 } nbx_counters;
 void nbx_get_counters(nbx_counters *out);
 void nbx_reset_counters(void);

@@ -45,6 +45,7 @@ class Oracle:
         L.ora_step_brute_force_mt.argtypes = [f, i32]
         L.ora_step_barnes_hut.argtypes = [f, f, i32]
         L.ora_bh_build.argtypes = []
+        L.ora_set_square_aabb.argtypes = [i32]
         L.ora_bh_node_count.restype = i32
         L.ora_bh_max_depth.restype = i32
         L.ora_bh_flatten.argtypes = [vp, i32]
@@ -110,6 +111,10 @@ class Oracle:
     # -- Barnes-Hut -------------------------------------------------------------------------
     def step_barnes_hut(self, theta: float, dt: float, nthreads: int = 1) -> None:
         self.L.ora_step_barnes_hut(theta, dt, nthreads)
+
+    def set_square_aabb(self, on: bool) -> None:
+        """Opt-in, NOT reference behaviour: the commented-out squared-up root box of rs-src/nbody.rs:400-407."""
+        self.L.ora_set_square_aabb(1 if on else 0)
 
     def bh_build(self) -> None:
         self.L.ora_bh_build()

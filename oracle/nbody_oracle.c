@@ -406,6 +406,8 @@ static void count_walk(const Node *n, float px, float py, float theta, uint64_t 
 
 static Node g_root;
 static int g_tree_valid = 0;
+static int g_square_aabb = 0;
+void ora_set_square_aabb(int32_t on) { g_square_aabb = on != 0; }
 
 /* rs-src/nbody.rs:388-417 -- tight, non-square AABB, then insertion in particle index order */
 void ora_bh_build(void)
@@ -420,6 +422,12 @@ void ora_bh_build(void)
         y1 = p->py < y1 ? p->py : y1;
         x2 = p->px > x2 ? p->px : x2;
         y2 = p->py > y2 ? p->py : y2;
+    }
+    if (g_square_aabb) {
+        /* NOT the reference's behaviour: its author's commented-out variant, rs-src/nbody.rs:400-407, kept as an
+         * opt-in so that the product's nbx_set_square_aabb(1) has something to be checked against */
+        if (x2 - x1 > y2 - y1) y2 = y1 + (x2 - x1);
+        else x2 = x1 + (y2 - y1);
     }
     node_new(&g_root, x1, y1, x2, y2);
     for (int32_t i = 0; i < g_n; i++) insert(&g_root, g_p[i].px, g_p[i].py, g_p[i].m, 0);

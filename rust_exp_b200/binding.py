@@ -45,6 +45,8 @@ SYMBOLS = {
     "nbx_set_stream": (i32, [vp]),
     "nbx_synchronize": (i32, []),
     "nbx_set_async": (i32, [i32]),
+    "nbx_set_integrator": (i32, [i32]),
+    "nbx_set_square_aabb": (i32, [i32]),
     "nbx_set_peer_timeout_ms": (i32, [i32]),
     "nbx_seed": (None, [u64]),
     "nbx_tune": (i32, [i32, i32, i32]),
@@ -76,6 +78,7 @@ SYMBOLS = {
 }
 
 MODE_FAST, MODE_EXACT = 0, 1
+INTEGRATOR_EULER, INTEGRATOR_LEAPFROG_KDK = 0, 1
 TRANSPORT_P2P_DIRECT, TRANSPORT_P2P_GATHER, TRANSPORT_NCCL = 0, 1, 2
 LAW3_NEWTON, LAW3_REF = 0, 1
 PHASES = ("force", "integrate", "aabb", "keys", "sort", "build", "com", "xrank")
@@ -91,6 +94,8 @@ class Counters(C.Structure):
         ("steps", u64),
         ("bh_pops", u64),
         ("bh_pop_lanes", u64),
+        ("bh_part_bodies", u64),
+        ("bh_sort_levels", u64),
     ]
 
 
@@ -185,6 +190,12 @@ class NBodyLib:
 
     def synchronize(self) -> None:
         self._chk(self.L.nbx_synchronize(), "nbx_synchronize")
+
+    def set_integrator(self, integrator: int) -> None:
+        self._chk(self.L.nbx_set_integrator(integrator), "nbx_set_integrator")
+
+    def set_square_aabb(self, on: bool) -> None:
+        self._chk(self.L.nbx_set_square_aabb(1 if on else 0), "nbx_set_square_aabb")
 
     def set_async(self, on: bool) -> None:
         self._chk(self.L.nbx_set_async(1 if on else 0), "nbx_set_async")

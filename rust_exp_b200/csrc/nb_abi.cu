@@ -23,6 +23,7 @@ static void replace_set_begin(Engine& e, int n) {
     if (e.dist && e.world > 1) dist_wait_all(e, e.step_count);  // peers may still be reading our arena
     e.n = n;
     e.set_gen++;
+    e.kdk_pending = 0.f;
     e.mirror_mass_valid = false;
     ensure_capacity(e, n);
 }
@@ -100,6 +101,7 @@ void b200_nb_draw(int32_t w, int32_t h, uint32_t* fb) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
+    kdk_close(e);   // the velocity tails are drawn from synchronised velocities
     draw_to_host(e, w, h, fb);
 }
 
@@ -116,6 +118,7 @@ void b200_nb_get_particles(float* aos5_out, int32_t n) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
+    kdk_close(e);
     if (e.dist && e.world > 1) dist_wait_all(e, e.step_count);
     state_download_aos(e, aos5_out, n);
     if (e.dist && e.world > 1) {
@@ -129,6 +132,7 @@ int32_t nbx_get_particles_local(float* aos5_out_full, int32_t n) {
     NB_LOCK();
     Engine& e = engine();
     ensure_init(e);
+    kdk_close(e);
     state_download_local(e, aos5_out_full, n);
     if (e.bh) bh_poll(e);
     return 0;
@@ -175,6 +179,7 @@ void nbx_shutdown(void) {
     e.mirror_cap = e.partial_cap = e.force_cap = e.stage_dev_cap = 0;
     e.lay = ArenaLayout(); e.L_cap = 0; e.arena_cap_bytes = 0; e.n = 0; e.dist = false; e.rank = 0; e.world = 1; e.peers_mapped = false;
     e.cur = 0; e.step_count = 0; e.mode = NBX_MODE_FAST; e.tune = Tuning(); e.ctr = nbx_counters{};
+    e.integrator = NBX_INTEGRATOR_EULER; e.kdk_pending = 0.f; e.kdk_theta = 0.f; e.square_aabb = 0;
     e.transport = NBX_TRANSPORT_P2P_DIRECT; e.max_particles = 0; e.mirror_mass_valid = false; e.bh_partition = 0;
     e.bh_count = false; e.phase_timing = false; e.ev_slot = 0; e.bh_lay = BhArenaLayout();
     for (int p = 0; p < NBX_NUM_PHASES; p++) e.ev_count[p] = 0;
@@ -192,6 +197,24 @@ int32_t nbx_set_peer_timeout_ms(int32_t ms) {
     return 0;
 }
 
+int32_t nbx_set_integrator(int32_t integrator) {
+    NB_LOCK();
+    Engine& e = engine();
+    if (integrator != NBX_INTEGRATOR_EULER && integrator != NBX_INTEGRATOR_LEAPFROG_KDK) {
+        set_error("unknown integrator %d", integrator);
+        return -1;
+    }
+    if (e.inited) kdk_close(e);   // leave the old scheme with synchronised velocities
+    e.integrator = integrator;
+    e.kdk_pending = 0.f;
+    return 0;
+}
+int32_t nbx_set_square_aabb(int32_t enable) {
+    NB_LOCK();
+    engine().square_aabb = enable != 0;
+    return 0;
+}
+
 const char* nbx_last_error(void) { return last_error(); }
 const char* nbx_version(void) { return "nbody_b200 0.1 (sm_100a)"; }
 
@@ -201,6 +224,7 @@ int32_t nbx_set_mode(int32_t mode) {
         set_error("unknown mode %d", mode);
         return -1;
     }
+    if (engine().inited) kdk_close(engine());
     engine().mode = mode;
     return 0;
 }

@@ -194,6 +194,8 @@ struct BhWork {
         uint64_t alloc_gen = 0;
         size_t L = 0;
         int sort_levels = 0;
+        float kick = 0.f;
+        int square = 0;
     } graph[2];
     uint64_t alloc_gen = 0;          // bumped whenever a buffer a captured graph points at is (re)allocated
     bool capturing = false;
@@ -270,6 +272,17 @@ __global__ void bh_aabb_kernel(const float* __restrict__ x, const float* __restr
         atomicMax(&st->aabb_enc[2], mxx);
         atomicMax(&st->aabb_enc[3], mxy);
     }
+}
+
+// opt-in (nbx_set_square_aabb): the reference author's commented-out variant, rs-src/nbody.rs:400-407
+//     if x2 - x1 > y2 - y1 { y2 = y1 + (x2 - x1) } else { x2 = x1 + (y2 - y1) }
+__device__ __forceinline__ void square_up(int* enc) {
+    const float x1 = ord2f(enc[0]), y1 = ord2f(enc[1]), x2 = ord2f(enc[2]), y2 = ord2f(enc[3]);
+    if (__fsub_rn(x2, x1) > __fsub_rn(y2, y1)) enc[3] = f2ord(__fadd_rn(y1, __fsub_rn(x2, x1)));
+    else enc[2] = f2ord(__fadd_rn(x1, __fsub_rn(y2, y1)));
+}
+__global__ void bh_square_aabb_kernel(BhStatus* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) square_up(st->aabb_enc);
 }
 
 // ---- keys: the reference's midpoint recursion, kLevels deep ------------------------------------------
@@ -1261,6 +1274,7 @@ static void bh_forces(Engine& e, float theta) {
         bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
         bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
         e.ctr.kernel_launches += 2;
+        if (e.square_aabb) { bh_square_aabb_kernel<<<1, 32, 0, s>>>(w.status); e.ctr.kernel_launches++; }
     }
     if (e.mode == NBX_MODE_EXACT) {
         bool done = false;
@@ -1310,6 +1324,7 @@ static void bh_forces(Engine& e, float theta) {
                 PhaseScope ps(e, 5);
                 bh_reset_kernel<<<1, 32, 0, s>>>(w.status);
                 bh_aabb_kernel<<<std::min(G, e.num_sms * 4), T, 0, s>>>(gp.x, gp.y, n, w.status);
+                if (e.square_aabb) { bh_square_aabb_kernel<<<1, 32, 0, s>>>(w.status); e.ctr.kernel_launches++; }
                 bh_build_serial_kernel<<<1, 32, 0, s>>>(gp.x, gp.y, gp.m, n, w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
                 bh_finalize_exact_kernel<<<(w.cap_nodes + T - 1) / T, T, 0, s>>>(w.cap_nodes, w.ndata, w.nbounds, w.nchild, w.status);
                 e.ctr.kernel_launches += 4;
@@ -1422,7 +1437,7 @@ __global__ void bhp_boxes_publish_kernel(const BhStatus* st, PeerArenas peers, s
 }
 // wait for all G boxes, reduce (exact), store the global box where the key / build / top kernels read it
 __global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size_t off_flags, int world, uint32_t epoch,
-                                        unsigned long long timeout_ns, BhStatus* st_part, BhStatus* st_global) {
+                                        unsigned long long timeout_ns, BhStatus* st_part, BhStatus* st_global, int square) {
     const int g = threadIdx.x;
     if (g < world)
         wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + kFlagBoxes * 64 + g, epoch, timeout_ns, g, "Barnes-Hut boxes");
@@ -1434,8 +1449,9 @@ __global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size
             mnx = min(mnx, b[4 * r + 0]); mny = min(mny, b[4 * r + 1]);
             mxx = max(mxx, b[4 * r + 2]); mxy = max(mxy, b[4 * r + 3]);
         }
-        st_part->aabb_enc[0] = mnx; st_part->aabb_enc[1] = mny; st_part->aabb_enc[2] = mxx; st_part->aabb_enc[3] = mxy;
-        st_global->aabb_enc[0] = mnx; st_global->aabb_enc[1] = mny; st_global->aabb_enc[2] = mxx; st_global->aabb_enc[3] = mxy;
+        int enc[4] = {mnx, mny, mxx, mxy};
+        if (square) square_up(enc);
+        for (int k = 0; k < 4; k++) { st_part->aabb_enc[k] = enc[k]; st_global->aabb_enc[k] = enc[k]; }
     }
 }
 
@@ -1484,19 +1500,30 @@ struct MergeArgs {
     size_t stride;
     BhStatus* st;
 };
+constexpr int kMergeSamples = 512;   // per run: every S-th key cached in shared memory (S = power of two, sized per step)
 __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
     __shared__ int cnt[kMaxRanks], off[kMaxRanks + 1];
+    __shared__ int s_shift;
+    __shared__ unsigned long long samp[kMaxRanks][kMergeSamples];
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(a.arena + a.off_in_key);
+    const float4* recs = reinterpret_cast<const float4*>(a.arena + a.off_in_rec);
     if (threadIdx.x == 0) {
         const int* ci = reinterpret_cast<const int*>(a.arena + a.off_count_in);
-        int o = 0;
-        for (int s = 0; s < a.nparts; s++) { cnt[s] = ci[s]; off[s] = o; o += cnt[s]; }
+        int o = 0, mx = 0;
+        for (int s = 0; s < a.nparts; s++) { cnt[s] = ci[s]; off[s] = o; o += cnt[s]; mx = max(mx, cnt[s]); }
         off[a.nparts] = o;
+        int sh = 0;
+        while (((mx + (1 << sh) - 1) >> sh) > kMergeSamples) sh++;
+        s_shift = sh;
         if (blockIdx.x == 0) a.st->n_part = o;
     }
     __syncthreads();
-    const int n = off[a.nparts];
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(a.arena + a.off_in_key);
-    const float4* recs = reinterpret_cast<const float4*>(a.arena + a.off_in_rec);
+    const int n = off[a.nparts], sh = s_shift, S = 1 << sh;
+    for (int r = 0; r < a.nparts; r++) {
+        const int ns = (cnt[r] + S - 1) >> sh;
+        for (int k = threadIdx.x; k < ns; k += blockDim.x) samp[r][k] = keys[static_cast<size_t>(r) * a.R + (static_cast<size_t>(k) << sh)];
+    }
+    __syncthreads();
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += gridDim.x * blockDim.x) {
         if (t == n) {   // sentinel of the exclusive scans over n + 1 entries
             a.w3[n] = 0.0; a.w3[a.stride + n] = 0.0; a.w3[2 * a.stride + n] = 0.0;
@@ -1509,11 +1536,18 @@ __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
         int pos = i;
         for (int r = 0; r < a.nparts; r++) {
             if (r == s || cnt[r] == 0) continue;
-            const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
-            int l = 0, h = cnt[r];
-            if (r < s) { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] <= k) l = mid + 1; else h = mid; } }   // ties: lower source first
-            else       { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] < k) l = mid + 1; else h = mid; } }
-            pos += l;
+            // rank of k in run r: elements < k, or <= k for runs of lower source rank (ties: lower source first).
+            // Coarse step on the cached samples, fine step inside one S-wide window of the run.
+            const bool le = r < s;
+            const int ns = (cnt[r] + S - 1) >> sh;
+            int l = 0, h = ns;
+            while (l < h) { const int mid = (l + h) >> 1; const unsigned long long v = samp[r][mid]; if (le ? v <= k : v < k) l = mid + 1; else h = mid; }
+            if (l > 0) {
+                const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
+                int lo2 = ((l - 1) << sh) + 1, hi2 = min(l << sh, cnt[r]);
+                while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; const unsigned long long v = kr[mid]; if (le ? v <= k : v < k) lo2 = mid + 1; else hi2 = mid; }
+                pos += lo2;
+            }
         }
         const float4 rc = recs[static_cast<size_t>(s) * a.R + i];
         a.mkeys[pos] = k;
@@ -1683,12 +1717,14 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
 struct PartStatusPtrs { BhStatus* p[kMaxRanks]; };
 __global__ void bhp_fold_status_kernel(BhStatus* global, PartStatusPtrs parts, int nlocal) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        int deep = 0, ovf = 0, run = 0;
+        int deep = 0, ovf = 0, run = 0, np = 0;
         for (int r = 0; r < nlocal; r++) {
+            np += parts.p[r]->n_part;
             deep += parts.p[r]->n_deep; ovf |= parts.p[r]->overflow; run = max(run, parts.p[r]->sort_long_run);
             for (int d = 0; d <= kLevels; d++) global->delta_hist[d] += parts.p[r]->delta_hist[d];
         }
         global->n_deep += deep;
+        global->n_part = np;
         global->overflow |= ovf;
         global->sort_long_run = max(global->sort_long_run, run);
     }
@@ -1838,7 +1874,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PhaseScope ps(e, 7);
         for (int r = 0; r < nlocal; r++) {
             bhp_boxes_reduce_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_aabb, lay.off_flags, nparts, epoch, e.peer_timeout_ns,
-                                                     w.parts[r].status, w.status);
+                                                     w.parts[r].status, w.status, e.square_aabb);
             e.ctr.kernel_launches++;
         }
     }
@@ -1890,7 +1926,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             PartBufs& P = w.parts[r];
             const size_t stride = P.cap + 1;
             MergeArgs ma{P.arena, lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R, nparts, P.mkeys, P.sx, P.sy, P.sm, P.gidx, P.w3, stride, P.status};
-            bhp_merge_kernel<<<GE, T, 0, s>>>(ma);
+            bhp_merge_kernel<<<std::min(GE, e.num_sms * 4), T, 0, s>>>(ma);
             launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride, e.num_sms * 4);
             e.ctr.kernel_launches += 4;
         }
@@ -1969,14 +2005,18 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
 // round again (two steps later) or at any synchronising call, so stepping never stalls the host on the GPU.
 static int choose_sort_levels(const BhStatus& h, int n) {
     if (n < 8192) return kLevels;
-    // sorting on L levels leaves the neighbours that share >= L levels to the fix-up: keep those below n/128
-    unsigned long long tail = 0;
-    int L = 0;
-    for (int d = kLevels; d >= 0; d--) {
-        tail += h.delta_hist[d];
-        if (tail * 128ull > static_cast<unsigned long long>(n)) { L = d + 1; break; }
-    }
-    return std::max(6, std::min(kLevels, L + 1));
+    // Sorting on L levels leaves the neighbours that share >= L levels to the fix-up (cheap for pairs and short runs).
+    // tail[L] = number of such neighbour pairs.  Prefer the 32-bit path (L <= 16): take the smallest L that leaves at
+    // most n/32 pairs; if that needs more than 16 levels, 16 is still taken as long as no more than n/4 pairs remain.
+    unsigned long long tail[kLevels + 2] = {};
+    for (int d = kLevels; d >= 0; d--) tail[d] = tail[d + 1] + h.delta_hist[d];
+    int L = kLevels;
+    while (L > 6 && tail[L - 1] * 32ull <= static_cast<unsigned long long>(n)) L--;
+    if (L > 16 && tail[16] * 4ull <= static_cast<unsigned long long>(n)) L = 16;
+    if (getenv("NB_DEBUG_SORT"))
+        fprintf(stderr, "nbody_b200: sort depth: n=%d tail[12]=%llu tail[14]=%llu tail[16]=%llu tail[18]=%llu tail[20]=%llu -> %d levels\n", n,
+                tail[12], tail[14], tail[16], tail[18], tail[20], L);
+    return L;
 }
 static void process_slot(Engine& e, BhWork& w, int k, bool wait) {
     BhWork::StatusSlot& sl = w.slot[k];
@@ -2000,6 +2040,8 @@ static void process_slot(Engine& e, BhWork& w, int k, bool wait) {
     e.ctr.bh_nodes_visited += h.visited;
     e.ctr.bh_pops += h.pops;
     e.ctr.bh_pop_lanes += h.pop_lanes;
+    e.ctr.bh_part_bodies = sl.partitioned ? static_cast<uint64_t>(h.n_part) : static_cast<uint64_t>(sl.n);
+    e.ctr.bh_sort_levels = static_cast<uint64_t>(w.sort_levels);
     for (int q = 0; q < 33; q++) w.pop_hist[q] += h.pop_hist[q];
     if (e.mode == NBX_MODE_FAST && sl.n > 0) w.sort_levels = choose_sort_levels(h, sl.n);
 }
@@ -2017,6 +2059,7 @@ static void status_begin(Engine& e, BhWork& w) {
     w.cur_slot = k;
     w.status_host = w.slot[k].host;
     if (w.seen_set_gen != e.set_gen) { w.seen_set_gen = e.set_gen; w.sort_levels = kLevels; }
+    if (const char* f = getenv("NB_SORT_LEVELS")) { const int v = atoi(f); if (v >= 1 && v <= kLevels) w.sort_levels = v; }   // experiments
 }
 // end of the device work of a Barnes-Hut call: queue the status copy behind it
 static void status_commit(Engine& e, BhWork& w, bool partitioned) {
@@ -2059,6 +2102,7 @@ static bool bh_graph_eligible(const Engine& e) {
 void bh_step(Engine& e, float theta, float dt) {
     if (e.n == 0) return;
     BhWork& w = work(e);
+    e.kdk_theta = theta;
     if (bh_graph_eligible(e)) {
         ensure_status(w);
         status_begin(e, w);
@@ -2073,7 +2117,8 @@ void bh_step(Engine& e, float theta, float dt) {
         BhWork::GraphSlot& g = w.graph[e.cur];
         // every pointer and scalar a captured launch carries is a function of this key (alloc_gen covers the workspace)
         const bool hit = g.exec && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
-                         g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L && g.sort_levels == w.sort_levels;
+                         g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L && g.sort_levels == w.sort_levels &&
+                         g.kick == kick_dt(e, dt) && g.square == e.square_aabb;
         if (!hit) {
             // Re-capture (host-only work, ~20 nodes) and patch the instantiated graph in place: a theta / dt change
             // from the reference UI (hs-src/RustNBodyExperiment.hs:88-93) or a reallocation only changes kernel
@@ -2081,6 +2126,7 @@ void bh_step(Engine& e, float theta, float dt) {
             // it also accepts.  Only if the update is refused is the graph re-instantiated.
             const int cur0 = e.cur;
             const uint64_t l0 = e.ctr.kernel_launches;
+            const float kick0 = kick_dt(e, dt);
             cudaGraph_t graph = nullptr;
             w.capturing = true;
             NB_CUDA(cudaStreamBeginCapture(e.stream, cudaStreamCaptureModeThreadLocal));
@@ -2096,12 +2142,13 @@ void bh_step(Engine& e, float theta, float dt) {
             if (!updated) NB_CUDA(cudaGraphInstantiate(&g.exec, graph, 0));
             NB_CUDA(cudaGraphDestroy(graph));
             g.n = e.n; g.cur = cur0; g.theta = theta; g.dt = dt; g.stream = e.stream; g.arena = e.arena.base;
-            g.alloc_gen = w.alloc_gen; g.L = e.lay.L; g.sort_levels = w.sort_levels;
+            g.alloc_gen = w.alloc_gen; g.L = e.lay.L; g.sort_levels = w.sort_levels; g.kick = kick0; g.square = e.square_aabb;
             g.launches = e.ctr.kernel_launches - l0;
             // the capture already advanced the host-side state exactly like a replay does below
         } else {
             e.ctr.kernel_launches += g.launches;
             e.cur ^= 1;
+            if (e.integrator == NBX_INTEGRATOR_LEAPFROG_KDK) e.kdk_pending = 0.5f * dt;
             w.acc_src = w.acc;
             w.last_partitioned = false;
             TreeTable tt{};

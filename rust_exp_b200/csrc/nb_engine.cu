@@ -181,6 +181,7 @@ static void fill_local(Engine& e, AllPairsArgs& a) {
 // rs-src/nbody.rs:106-162
 void step_brute_force(Engine& e, float dt) {
     if (e.n == 0) return;
+    e.kdk_theta = 0.f;
     AllPairsArgs a{};
     allpairs_plan(e, a);
     fill_local(e, a);
@@ -207,6 +208,18 @@ void step_brute_force(Engine& e, float dt) {
     dist_signal_step_done(e);
     e.ctr.steps++;
     if (e.phase_timing) e.ev_slot++;
+}
+
+// Leapfrog (KDK) keeps v at the half step between steps.  Before anything reads the state, the owed closing half kick
+// v += (dt/2) a(x) is applied with one force evaluation by the method of the last step; stepping then continues from a
+// synchronised (x, v), which is algebraically the same kick-drift-kick sequence.
+void kdk_close(Engine& e) {
+    if (e.integrator != NBX_INTEGRATOR_LEAPFROG_KDK || e.kdk_pending == 0.f || e.n == 0) return;
+    const float h = e.kdk_pending;
+    e.kdk_pending = 0.f;
+    if (e.kdk_theta == 0.f) accelerations_local(e);
+    else bh_accelerations(e, e.kdk_theta, e.force);
+    launch_kick(e, e.force, h);
 }
 
 // accelerations of the local shard into e.force (as a_i), no state change

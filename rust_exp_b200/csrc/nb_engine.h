@@ -163,6 +163,12 @@ struct Engine {
     uint64_t peer_timeout_ns = 30000000000ull;   // device-side waits on peers trap after this long (0 = never)
     int cur = 0;                     // current position buffer
     uint32_t step_count = 0;         // steps completed (also the cross-rank flag value)
+    // opt-in integrator (rs-src/nbody.rs:449 TODO): leapfrog kick-drift-kick, FAST mode.  Velocities are kept at the half
+    // step between steps; kdk_pending = the half kick (dt/2) still owed, applied before any read-back (kdk_close).
+    int integrator = NBX_INTEGRATOR_EULER;
+    float kdk_pending = 0.f;
+    float kdk_theta = 0.f;           // force method of the last step (0 = all-pairs), used for the closing kick
+    int square_aabb = 0;             // opt-in (rs-src/nbody.rs:400-407): square up the root box of the quadtree
     uint64_t set_gen = 0;            // bumped whenever the particle set is replaced (set / generators)
     // full mirror of all shards (GATHER / NCCL transports and Barnes-Hut): x,y,m of G*L bodies
     float* mirror = nullptr;
@@ -223,6 +229,9 @@ void state_download_aos(Engine& e, float* aos5, int n);
 void state_download_local(Engine& e, float* aos5_full, int n);
 void launch_integrate_fast(Engine& e, const float2* partial, int nslices, float dt, bool kill);
 void launch_integrate_exact(Engine& e, const float2* force, float dt, bool kill);
+void launch_kick(Engine& e, const float2* acc, float h);
+inline float kick_dt(const Engine& e, float dt) { return e.integrator == NBX_INTEGRATOR_LEAPFROG_KDK ? e.kdk_pending + 0.5f * dt : dt; }
+void kdk_close(Engine& e);   // nb_engine.cu: apply the owed half kick (one force evaluation) so that v is synchronised with x
 void launch_fill_zero_f32(Engine& e, float* p, size_t n);
 void generate_random_disk(Engine& e, int n);
 void generate_stable_orbits(Engine& e, int n, float rmin, float rmax);

@@ -115,7 +115,9 @@ void state_download_local(Engine& e, float* aos5_full, int n) {
 // FAST: a = sum of per-slice partial accelerations in ascending slice order (deterministic), then
 // v += dt*a ; p += dt*v   (rs-src/nbody.rs:155-159 with F/m folded into a), optional velocity kill
 // (rs-src/nbody.rs:466-471).
-__global__ void integrate_fast_kernel(const float2* __restrict__ partial, int nslices, int L, int count, float dt,
+// dt_kick != dt only for the opt-in leapfrog (kick-drift-kick): the kick then closes the previous step's half kick and
+// opens this step's, dt_kick = dt_prev/2 + dt/2 (nb_engine.cu::kick_dt).
+__global__ void integrate_fast_kernel(const float2* __restrict__ partial, int nslices, int L, int count, float dt_kick, float dt,
                                       int kill, const float* __restrict__ xc, const float* __restrict__ yc,
                                       float* __restrict__ xn, float* __restrict__ yn, float* __restrict__ vx,
                                       float* __restrict__ vy) {
@@ -127,8 +129,8 @@ __global__ void integrate_fast_kernel(const float2* __restrict__ partial, int ns
         ax += p.x;
         ay += p.y;
     }
-    float qx = fmaf(dt, ax, vx[i]);
-    float qy = fmaf(dt, ay, vy[i]);
+    float qx = fmaf(dt_kick, ax, vx[i]);
+    float qy = fmaf(dt_kick, ay, vy[i]);
     const float px = fmaf(dt, qx, xc[i]);
     const float py = fmaf(dt, qy, yc[i]);
     if (kill && (fabsf(px) > kKillLimit || fabsf(py) > kKillLimit)) { qx = 0.f; qy = 0.f; }
@@ -163,13 +165,30 @@ void launch_integrate_fast(Engine& e, const float2* partial, int nslices, float 
     const int nxt = e.cur ^ 1;
     if (count > 0) {
         integrate_fast_kernel<<<(count + kBlk - 1) / kBlk, kBlk, 0, e.stream>>>(
-            partial, nslices, static_cast<int>(e.lay.L), count, dt, kill ? 1 : 0, e.arena.x(e.lay, e.cur),
+            partial, nslices, static_cast<int>(e.lay.L), count, kick_dt(e, dt), dt, kill ? 1 : 0, e.arena.x(e.lay, e.cur),
             e.arena.y(e.lay, e.cur), e.arena.x(e.lay, nxt), e.arena.y(e.lay, nxt), e.arena.vx(e.lay),
             e.arena.vy(e.lay));
         NB_CUDA(cudaGetLastError());
         e.ctr.kernel_launches++;
     }
+    if (e.integrator == NBX_INTEGRATOR_LEAPFROG_KDK) e.kdk_pending = 0.5f * dt;   // the closing half kick is still owed
     e.cur = nxt;
+}
+
+// v += h * a for the local shard: the closing half kick of the leapfrog, applied before state is read back
+__global__ void kick_kernel(const float2* __restrict__ acc, int count, float h, float* __restrict__ vx, float* __restrict__ vy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const float2 a = acc[i];
+    vx[i] = fmaf(h, a.x, vx[i]);
+    vy[i] = fmaf(h, a.y, vy[i]);
+}
+void launch_kick(Engine& e, const float2* acc, float h) {
+    const int count = local_count(e);
+    if (count <= 0) return;
+    kick_kernel<<<(count + kBlk - 1) / kBlk, kBlk, 0, e.stream>>>(acc, count, h, e.arena.vx(e.lay), e.arena.vy(e.lay));
+    NB_CUDA(cudaGetLastError());
+    e.ctr.kernel_launches++;
 }
 
 void launch_integrate_exact(Engine& e, const float2* force, float dt, bool kill) {
