@@ -803,8 +803,9 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 // no test: their contribution is an exact zero because EPS > 0.
 // Lanes outside an entry's mask run with theta^2 = NaN: both `q < t` and the derived open mask are then false
 // without any per-child predicate logic.
-template <bool COUNT, bool PARTS>
-__global__ void __launch_bounds__(kTravWarps * 32, 6) bh_traverse_fast_kernel(
+constexpr int kSparseLanes = 8;   // entries that concern at most this many bodies are batched four at a time
+template <bool COUNT, bool PARTS, bool SPARSE>
+__global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
     float theta2, BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
@@ -838,8 +839,103 @@ __global__ void __launch_bounds__(kTravWarps * 32, 6) bh_traverse_fast_kernel(
             if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
         }
         while (sp > 0) {
+            const uint2 e = s[sp - 1];
+            if (SPARSE && __popc(e.y) <= kSparseLanes) {
+                // ---- sparse pass: up to four entries that each concern <= 8 bodies are evaluated together, one entry per
+                // octet of lanes, lane j of an octet standing in for the j-th body of its entry (siblings pushed by one
+                // pop sit next to each other on the stack, so the batch usually fills).  Same arithmetic per (body, child).
+                uint2 E1 = make_uint2(0u, 0u), E2 = E1, E3 = E1;
+                int k = 1;
+                if (sp >= 2) {
+                    E1 = s[sp - 2];
+                    if (__popc(E1.y) <= kSparseLanes) {
+                        k = 2;
+                        if (sp >= 3) {
+                            E2 = s[sp - 3];
+                            if (__popc(E2.y) <= kSparseLanes) {
+                                k = 3;
+                                if (sp >= 4) { E3 = s[sp - 4]; if (__popc(E3.y) <= kSparseLanes) k = 4; }
+                            }
+                        }
+                    }
+                }
+                if (k < 2) E1.y = 0u;
+                if (k < 3) E2.y = 0u;
+                if (k < 4) E3.y = 0u;
+                sp -= k;
+                __syncwarp();
+                const int oct = lane >> 3, j = lane & 7;
+                const uint2 eo = oct == 0 ? e : (oct == 1 ? E1 : (oct == 2 ? E2 : E3));
+                const unsigned b = __fns(eo.y, 0u, j + 1);          // lane that owns the j-th body of this octet's entry
+                const bool act = b < 32u;
+                const float qx = __shfl_sync(0xffffffffu, px, act ? b : lane), qy = __shfl_sync(0xffffffffu, py, act ? b : lane);
+                const float thx = act ? theta2 : qnan;
+                unsigned part = 0, bi = eo.x;
+                const float4* __restrict__ nb4;
+                if (PARTS) {
+                    part = eo.x >> kPartShift; bi = eo.x & ((1u << kPartShift) - 1u);
+                    nb4 = tt.blk[part] + 4 * static_cast<size_t>(bi);
+                } else {
+                    nb4 = tt.blk[0] + 4 * static_cast<size_t>(bi);
+                }
+                const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), Q = __ldg(nb4 + 3);
+                const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy);
+                const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), nqx), dx23 = __fadd2_rn(make_float2(X.z, X.w), nqx);
+                const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), nqy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), nqy);
+                const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
+                const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
+                const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
+                const float2 t01 = __fmul2_rn(d01, make_float2(thx, thx)), t23 = __fmul2_rn(d23, make_float2(thx, thx));
+                const bool a0 = Q.x < t01.x, a1 = Q.y < t01.y, a2 = Q.z < t23.x, a3 = Q.w < t23.y;
+                float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
+                float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
+                c01.x = a0 ? c01.x : 0.f; c01.y = a1 ? c01.y : 0.f;
+                c23.x = a2 ? c23.x : 0.f; c23.y = a3 ? c23.y : 0.f;
+                const float2 tx = __ffma2_rn(c23, dx23, __fmul2_rn(c01, dx01)), ty = __ffma2_rn(c23, dy23, __fmul2_rn(c01, dy01));
+                const float cax = tx.x + tx.y, cay = ty.x + ty.y;
+                // hand every (entry, body) contribution back to the lane that owns the body
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    const unsigned mo = o == 0 ? e.y : (o == 1 ? E1.y : (o == 2 ? E2.y : E3.y));
+                    if (o < k) {
+                        const int srcl = 8 * o + __popc(mo & (lanebit - 1u));
+                        const float vx = __shfl_sync(0xffffffffu, cax, srcl), vy = __shfl_sync(0xffffffffu, cay, srcl);
+                        if (mo & lanebit) { ax.x += vx; ay.x += vy; }
+                    }
+                }
+                // bodies that did not accept child c must open it: one new lane mask per (entry, child), reduced inside the octet
+                const unsigned bit = act ? (1u << b) : 0u;
+                const unsigned omask = 0xffu << (8 * oct);
+                const unsigned n0 = __reduce_or_sync(omask, a0 ? 0u : bit), n1 = __reduce_or_sync(omask, a1 ? 0u : bit);
+                const unsigned n2 = __reduce_or_sync(omask, a2 ? 0u : bit), n3 = __reduce_or_sync(omask, a3 ? 0u : bit);
+                const int cnt = (n0 != 0u) + (n1 != 0u) + (n2 != 0u) + (n3 != 0u);
+                const int c0 = __shfl_sync(0xffffffffu, cnt, 0), c1 = __shfl_sync(0xffffffffu, cnt, 8);
+                const int c2 = __shfl_sync(0xffffffffu, cnt, 16), c3 = __shfl_sync(0xffffffffu, cnt, 24);
+                if (COUNT) {
+                    n_vis += act ? 4 : 0;
+                    n_int += (a0 && M.x != 0.f && !(X.x == qx && Y.x == qy)) + (a1 && M.y != 0.f && !(X.y == qx && Y.y == qy)) +
+                             (a2 && M.z != 0.f && !(X.z == qx && Y.z == qy)) + (a3 && M.w != 0.f && !(X.w == qx && Y.w == qy));
+                    const int lanes = __popc(e.y) + __popc(E1.y) + __popc(E2.y) + __popc(E3.y);
+                    if (lane == 0) { n_pop++; n_lane += lanes; atomicAdd(&st->pop_hist[lanes], 1ull); }
+                }
+                my_pops++;
+                if (c0 + c1 + c2 + c3) {
+                    // reverse octet order: octet 0 held the former top of the stack, its children end up on top again;
+                    // inside an octet child 3 lowest, child 0 on top.  Lanes 0..3 of an octet store one child each.
+                    const int base = sp + (oct < 3 ? c3 : 0) + (oct < 2 ? c2 : 0) + (oct < 1 ? c1 : 0);
+                    if (cnt != 0 && j < 4) {
+                        const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
+                        const unsigned nm = j == 0 ? n0 : (j == 1 ? n1 : (j == 2 ? n2 : n3));
+                        const unsigned cb = static_cast<unsigned>(j == 0 ? C.x : (j == 1 ? C.y : (j == 2 ? C.z : C.w)));
+                        const int above = ((j < 3) && n3 != 0u) + ((j < 2) && n2 != 0u) + ((j < 1) && n1 != 0u);
+                        if (nm != 0u) s[base + above] = make_uint2(cb, nm);
+                    }
+                    sp += c0 + c1 + c2 + c3;
+                }
+                __syncwarp();
+                continue;
+            }
             --sp;
-            const uint2 e = s[sp];
             __syncwarp();
             const bool act = (e.y & lanebit) != 0u;
             const float thx = act ? theta2 : qnan;
@@ -1120,7 +1216,7 @@ static int bh_partition_count(const Engine& e) {
 static int traverse_resident_blocks(Engine& e) {
     static int per_sm = 0;
     if (!per_sm) {
-        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false>, kTravWarps * 32, 0));
+        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, false>, kTravWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
     }
     return per_sm * e.num_sms;
@@ -1135,9 +1231,14 @@ static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, con
     const int blocks = std::min(want, traverse_resident_blocks(e));
     const bool parts = tt.shift != 31;
     const float th2 = theta * theta;
-#define NB_TRAV(C, P) bh_traverse_fast_kernel<C, P><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev)
-    if (e.bh_count) { if (parts) NB_TRAV(true, true); else NB_TRAV(true, false); }
-    else { if (parts) NB_TRAV(false, true); else NB_TRAV(false, false); }
+    // The sparse (octet) pass is an experiment that LOST (profiles/r02_walk_sparse_pass_ab.jsonl: 1.7x slower -- the
+    // sub-warp collectives it needs compile to WARPSYNC/ENDCOLLECTIVE loops): off unless NB_BH_SPARSE=1.
+    static const bool sparse = [] { const char* v = getenv("NB_BH_SPARSE"); return v ? atoi(v) != 0 : false; }();
+#define NB_TRAV(C, P, S) bh_traverse_fast_kernel<C, P, S><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev)
+#define NB_TRAV2(C, P) do { if (sparse) NB_TRAV(C, P, true); else NB_TRAV(C, P, false); } while (0)
+    if (e.bh_count) { if (parts) NB_TRAV2(true, true); else NB_TRAV2(true, false); }
+    else { if (parts) NB_TRAV2(false, true); else NB_TRAV2(false, false); }
+#undef NB_TRAV2
 #undef NB_TRAV
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
