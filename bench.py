@@ -644,7 +644,7 @@ def main():
     }
     for k in ("fp32_tflops", "fp32_frac_of_peak_all_gpus", "roofline_hbm", "steps_per_s", "interactions_per_s", "lane_efficiency",
               "lanes_per_pop_histogram", "pops_per_step", "interactions_per_step", "nodes_visited_per_step", "tree_nodes",
-              "walk_imbalance_max_over_mean", "cpu_baseline"):
+              "walk_imbalance_max_over_mean", "cpu_baseline", "per_rank", "sort_levels"):
         if k in m:
             line[k] = m[k]
     if w["kind"] == "bh":

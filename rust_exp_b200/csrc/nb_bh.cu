@@ -1659,11 +1659,26 @@ __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
     }
 }
 
-// one thread per level-kCutLevel cell of this part: publish its entry
-__global__ void bh_celltab_kernel(const BuildArgs a, const PartPlan* plan, int part, CellEntry* __restrict__ tab) {
-    const int c0 = plan->cut[part], c1 = plan->cut[part + 1];
-    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c1) return;
+// one thread per cut-level cell: the entries of the cells this part owns are stored into EVERY rank's copy of the cell
+// table (posted NVLink writes), and so is last step's walk cost of the cells this part walked then -- so that the top
+// build of every rank reads local memory only.
+struct PubArgs {
+    PeerArenas peers;
+    size_t off_celltab, off_workpub;
+    int nparts;
+    const PartPlan* plan;        // this step's partition
+    const PartPlan* plan_prev;   // last step's (the buffer the top build will overwrite with the next one)
+    int part;
+    const unsigned* work_prev;   // this rank's measured walk cost per cell, last step
+};
+__global__ void bh_celltab_kernel(const BuildArgs a, const PubArgs pub) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= kNumCells) return;
+    if (c >= pub.plan_prev->cut[pub.part] && c < pub.plan_prev->cut[pub.part + 1]) {
+        const unsigned wk = pub.work_prev[c];
+        for (int g = 0; g < pub.nparts; g++) reinterpret_cast<unsigned*>(pub.peers.a[g] + pub.off_workpub)[c] = wk;
+    }
+    if (c < pub.plan->cut[pub.part] || c >= pub.plan->cut[pub.part + 1]) return;
     const int n = build_n(a);
     const size_t stride = a.stride;
     auto lb = [&](unsigned long long cell) {   // first sorted body whose cell index is >= cell
@@ -1696,12 +1711,12 @@ __global__ void bh_celltab_kernel(const BuildArgs a, const PartPlan* plan, int p
             en.x = bx; en.y = by; en.m = bm;
         }
     }
-    tab[c] = en;
+    for (int g = 0; g < pub.nparts; g++) reinterpret_cast<CellEntry*>(pub.peers.a[g] + pub.off_celltab)[c] = en;
 }
 
 struct TopArgs {
-    const CellEntry* tab[kMaxRanks];   // tab[g] valid for cells [cut[g], cut[g+1])
-    const unsigned* work[kMaxRanks];   // work[g][c] = walk cost rank g measured for cell c on the previous step
+    const CellEntry* tab;              // the complete cell table (local copy, filled by all ranks)
+    const unsigned* work;              // work[c] = walk cost measured for cell c on the previous step (local copy)
     const PartPlan* plan;              // this step's partition
     PartPlan* plan_next;               // next step's, computed here from the same data on every rank
     int nparts;
@@ -1731,16 +1746,12 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
     __shared__ unsigned long long wts[kNumCells];
     __shared__ int s_top;
     for (int c = tid; c < kNumCells; c += blockDim.x) {
-        int g = 0;
-        while (g + 1 < a.nparts && c >= a.plan->cut[g + 1]) g++;
-        const CellEntry en = a.tab[g][c];
+        const CellEntry en = a.tab[c];
         a.tcount[offk + c] = en.count;
         a.tm3[offk + c] = en.M; a.tm3[kTopNodes + offk + c] = en.MX; a.tm3[2 * kTopNodes + offk + c] = en.MY;
         a.tleaf[offk + c] = make_float4(en.x, en.y, en.m, 0.f);
         a.tchild[offk + c] = en.child;
-        unsigned long long wt = kBodyWeight * static_cast<unsigned long long>(en.count);
-        for (int r = 0; r < a.nparts; r++) wt += a.work[r][c];
-        wts[c] = wt;
+        wts[c] = kBodyWeight * static_cast<unsigned long long>(en.count) + a.work[c];
     }
     if (tid == 0) s_top = 0;
     __syncthreads();
@@ -2046,7 +2057,9 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
                          static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, 1, nd, P.cap + 1};
             bh_owner_kernel<<<GE, T, 0, s>>>(ba, P.owner, P.status);
             bh_emit_kernel<<<std::min(GE, e.num_sms * 8), T, 0, s>>>(ba, P.owner, P.status);
-            bh_celltab_kernel<<<(kNumCells + 127) / 128, 128, 0, s>>>(ba, plan, part_id(r), reinterpret_cast<CellEntry*>(P.arena + lay.off_celltab));
+            PubArgs pa{peers, lay.off_celltab, lay.off_workpub, nparts, plan, plan_next, part_id(r),
+                       reinterpret_cast<const unsigned*>(P.arena + lay.off_cellwork) + ((epoch + 1u) & 1u) * kNumCells};
+            bh_celltab_kernel<<<(kNumCells + 127) / 128, 128, 0, s>>>(ba, pa);
             e.ctr.kernel_launches += 8;
         }
     }
@@ -2063,12 +2076,12 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PhaseScope ps(e, 6);
         TopArgs ta{};
         for (int g = 0; g < nparts; g++) {
-            ta.tab[g] = reinterpret_cast<const CellEntry*>(peers.a[g] + lay.off_celltab);
-            ta.work[g] = reinterpret_cast<const unsigned*>(peers.a[g] + lay.off_cellwork) + ((epoch + 1u) & 1u) * kNumCells;   // previous step's
             tt.blk[g] = reinterpret_cast<const float4*>(peers.a[g] + lay.off_nblk);
             tt.cblk[g] = reinterpret_cast<const int4*>(peers.a[g] + lay.off_ncblk);
             tt.acc[g] = real ? reinterpret_cast<float2*>(peers.a[g] + lay.off_acc) : (w.acc + static_cast<size_t>(g) * shard);
         }
+        ta.tab = reinterpret_cast<const CellEntry*>(w.parts[0].arena + lay.off_celltab);      // every local part holds a complete copy
+        ta.work = reinterpret_cast<const unsigned*>(w.parts[0].arena + lay.off_workpub);
         ta.plan = plan; ta.plan_next = plan_next; ta.nparts = nparts;
         ta.tcount = w.top.tcount; ta.tm3 = w.top.tm3; ta.tleaf = w.top.tleaf; ta.tchild = w.top.tchild;
         ta.blk = w.top.blk; ta.cblk = w.top.cblk;

@@ -49,7 +49,8 @@ struct ArenaLayout {
 //   aabb[G][4]          aabb[s] = rank s's local bounding box (ordered-int encoded), written by rank s
 //   count_in[G]         count_in[s] = bodies rank s delivered into inbox region s this step, written by rank s
 //   cellwork[2][cells]  walk cost per cut-level cell measured by this rank's walk (double-buffered by step parity)
-//   celltab[cells]      this rank's entries of the cut-level cell table (read by every rank's top-tree build)
+//   celltab[cells]      the cut-level cell table: every rank stores the entries of the cells it owns into EVERY rank's copy
+//   workpub[cells]      last step's walk cost per cell, stored here by whichever rank walked the cell (same broadcast)
 //   in_key/in_rec[G][R] inbox: region s receives the (key-sorted) bodies rank s owns by index that fall into THIS rank's
 //                       cells -- peer stores over NVLink (the all-to-all-v of the step)
 //   nblk / ncblk        this rank's subtree forest (block-SoA records + child indices), walked in place by the peers
@@ -62,7 +63,7 @@ struct BhArenaLayout {
     size_t R = 0;            // inbox region capacity (bodies) per source rank = shard capacity
     size_t cap_bodies = 0;   // most bodies one part may hold: the whole set (any imbalance is legal, only slow)
     int cap_blocks = 0;
-    size_t off_flags = 0, off_aabb = 0, off_count_in = 0, off_cellwork = 0, off_celltab = 0, off_in_key = 0, off_in_rec = 0,
+    size_t off_flags = 0, off_aabb = 0, off_count_in = 0, off_cellwork = 0, off_celltab = 0, off_workpub = 0, off_in_key = 0, off_in_rec = 0,
            off_nblk = 0, off_ncblk = 0, off_acc = 0, bytes = 0;
     void set(size_t shard_cap, int world_, size_t max_particles) {
         world = world_;
@@ -78,6 +79,7 @@ struct BhArenaLayout {
         off_count_in = take(kMaxRanks * sizeof(int));
         off_cellwork = take(2 * kBhNumCells * sizeof(unsigned));
         off_celltab = take(kBhNumCells * 64);
+        off_workpub = take(kBhNumCells * sizeof(unsigned));
         off_in_key = take(static_cast<size_t>(world) * R * 8);
         off_in_rec = take(static_cast<size_t>(world) * R * 16);
         off_nblk = take(cb * 64);
