@@ -495,7 +495,9 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
                     "theta": w["theta"], "sort_levels": lib.counters()["bh_sort_levels"]})
         if world > 1:
             # per-rank view of the partitioned step: bodies in each rank's domain part and its phase times
-            mine = {"rank": rank, "part_bodies": lib.counters()["bh_part_bodies"], **{k: round(v, 4) for k, v in phases.items()}}
+            mine = {"rank": rank, "part_bodies": lib.counters()["bh_part_bodies"], **{k: round(v, 4) for k, v in phases.items()},
+                    "xrank_boxes_bodies_trees_walks": [round(v, 4) for v in lib.phase_sub_ms("xrank")],
+                    "com_merge_top": [round(v, 4) for v in lib.phase_sub_ms("com")]}
             allr = [None] * world
             cx.dist.all_gather_object(allr, mine)
             out["per_rank"] = allr

@@ -181,6 +181,9 @@ int32_t nbx_bh_partition(int32_t parts);
 #define NBX_NUM_PHASES 8
 int32_t nbx_phase_timing(int32_t enable);
 int32_t nbx_get_phase_ms(float *out8);
+/* A phase may be entered several times per step (the cross-rank ordering points are: boxes, bodies, trees, walks): the
+ * per-entry averages behind the last nbx_get_phase_ms call, in entry order (4 floats). */
+int32_t nbx_get_phase_sub_ms(int32_t phase, float *out4);
 
 /* Accelerations only (no state update) of the current set with the current mode, a_i = F_i / m_i in
  * the reference's units, written to a HOST array of 2*n floats.  Used by sampled parity checks. */

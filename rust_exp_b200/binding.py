@@ -58,6 +58,7 @@ SYMBOLS = {
     "nbx_bh_partition": (i32, [i32]),
     "nbx_phase_timing": (i32, [i32]),
     "nbx_get_phase_ms": (i32, [vp]),
+    "nbx_get_phase_sub_ms": (i32, [i32, vp]),
     "nbx_accelerations": (i32, [vp, i32]),
     "nbx_bh_accelerations": (i32, [f32, vp, i32]),
     "nbx3_num_particles": (i32, []),
@@ -244,6 +245,11 @@ class NBodyLib:
         out = (C.c_float * 8)()
         self._chk(self.L.nbx_get_phase_ms(out), "nbx_get_phase_ms")
         return dict(zip(PHASES, [float(v) for v in out]))
+
+    def phase_sub_ms(self, phase: str) -> list:
+        out = (C.c_float * 4)()
+        self._chk(self.L.nbx_get_phase_sub_ms(PHASES.index(phase), out), "nbx_get_phase_sub_ms")
+        return [float(v) for v in out]
 
     def accelerations(self, n: int | None = None) -> np.ndarray:
         n = self.num_particles() if n is None else n

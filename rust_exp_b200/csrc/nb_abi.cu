@@ -335,6 +335,13 @@ int32_t nbx_get_phase_ms(float* out8) {
     return 0;
 }
 
+int32_t nbx_get_phase_sub_ms(int32_t phase, float* out4) {
+    NB_LOCK();
+    if (phase < 0 || phase >= NBX_NUM_PHASES) return -1;
+    memcpy(out4, engine().phase_sub_ms[phase], sizeof(float) * 4);   // filled by the last nbx_get_phase_ms
+    return 0;
+}
+
 int32_t nbx_accelerations(float* axy_out, int32_t n) {
     NB_LOCK();
     Engine& e = engine();

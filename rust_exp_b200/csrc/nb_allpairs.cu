@@ -99,6 +99,34 @@ __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const All
     const int n_items = n_itiles * total_slices;
     const int tiles_full_slice = a.slice_len / kTJ;
 
+    if (a.stage && blockIdx.x < 2 * (a.nseg - 1)) {
+        // ===== stager prologue: this CTA brings one half of one remote segment into local HBM, once per step =====
+        const int g = (a.my_rank + 1 + (blockIdx.x >> 1)) % a.nseg;
+        if (threadIdx.x == 0) wait_epoch(a.flags + g, a.wait_step, a.timeout_ns, g, "step");   // the peer finished writing it
+        __syncthreads();
+        const int L4 = a.seg_len >> 2, lo = (blockIdx.x & 1) ? (L4 >> 1) : 0, hi = (blockIdx.x & 1) ? L4 : (L4 >> 1);
+        const float4* __restrict__ sx = reinterpret_cast<const float4*>(a.src[g].x);
+        const float4* __restrict__ sy = reinterpret_cast<const float4*>(a.src[g].y);
+        const float4* __restrict__ sm4 = reinterpret_cast<const float4*>(a.src[g].m);
+        float4* dx = reinterpret_cast<float4*>(const_cast<float*>(a.dst[g].x));
+        float4* dy = reinterpret_cast<float4*>(const_cast<float*>(a.dst[g].y));
+        float4* dm = reinterpret_cast<float4*>(const_cast<float*>(a.dst[g].m));
+        for (int i = lo + threadIdx.x; i < hi; i += 4 * kThreads) {
+            float4 vx[4], vy[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int k = i + u * kThreads; if (k < hi) { vx[u] = sx[k]; vy[u] = sy[k]; } }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const int k = i + u * kThreads; if (k < hi) { dx[k] = vx[u]; dy[k] = vy[u]; } }
+            if (a.stage_mass) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const int k = i + u * kThreads; if (k < hi) dm[k] = sm4[k]; }
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(a.staged + g, 1u);
+    }
+
     if (warp == kComputeWarps) {
         // ===== producer warp: one elected lane feeds the ring for every item of this CTA =====
         if (lane == 0) {
@@ -110,7 +138,8 @@ __global__ void __launch_bounds__(kThreads, MINB) allpairs_fast_kernel(const All
                 const int sl = gslice - q * a.slices_per_seg;
                 const int g = (a.my_rank + q) % a.nseg;
                 if (a.flags != nullptr && !(seen_mask & (1u << g))) {
-                    wait_epoch(a.flags + g, a.wait_step, a.timeout_ns, g, "step");
+                    if (a.stage) wait_epoch(a.staged + g, a.stage_want, a.timeout_ns, g, "staged halves");   // local flag
+                    else wait_epoch(a.flags + g, a.wait_step, a.timeout_ns, g, "step");
                     seen_mask |= 1u << g;
                 }
                 const int j0 = sl * a.slice_len;

@@ -189,7 +189,30 @@ void dist_fill_segments(Engine& e, AllPairsArgs& a) {
             a.seg[g] = JSeg{av.x(e.lay, buf), av.y(e.lay, buf), av.m(e.lay)};
         }
         if (e.mode == NBX_MODE_FAST) {
-            a.flags = e.arena.flags(e.lay);  // the kernel's producer warp waits per segment
+            a.flags = e.arena.flags(e.lay);  // the kernel's producer warp (or its stagers) wait per segment
+            static const bool stage = [] { const char* v = getenv("NB_P2P_STAGE"); return v ? atoi(v) != 0 : true; }();
+            if (stage) {
+                // staged: each remote segment crosses NVLink once per step into the local mirror (2 stager CTAs per
+                // segment, inside the force kernel), then every j tile streams from local HBM
+                ensure_mirror(e);
+                if (!e.stage_flags) {
+                    NB_CUDA(cudaMalloc(&e.stage_flags, kMaxRanks * sizeof(uint32_t)));
+                    NB_CUDA(cudaMemsetAsync(e.stage_flags, 0, kMaxRanks * sizeof(uint32_t), e.stream));
+                    e.stage_epoch = 0;
+                }
+                e.stage_epoch++;
+                a.stage = 1;
+                a.staged = e.stage_flags;
+                a.stage_want = 2u * e.stage_epoch;
+                a.stage_mass = e.mirror_mass_valid ? 0 : 1;
+                const size_t L = e.lay.L;
+                for (int g = 0; g < e.world; g++) {
+                    a.src[g] = a.seg[g];
+                    a.dst[g] = JSeg{mirror_x(e) + g * L, mirror_y(e) + g * L, mirror_m(e) + g * L};
+                    if (g != e.rank) a.seg[g] = a.dst[g];
+                }
+                e.mirror_mass_valid = true;
+            }
         } else {
             dist_wait_all(e, e.step_count);
         }
@@ -208,6 +231,7 @@ void dist_fill_segments(Engine& e, AllPairsArgs& a) {
 }
 
 void dist_shutdown(Engine& e) {
+    if (e.stage_flags) { cudaFree(e.stage_flags); e.stage_flags = nullptr; e.stage_epoch = 0; }
     if (e.peers_mapped) {
         for (int g = 0; g < e.world; g++) {
             if (g != e.rank && e.peer[g].base) cudaIpcCloseMemHandle(e.peer[g].base);

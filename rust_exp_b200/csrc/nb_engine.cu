@@ -149,7 +149,7 @@ PhaseScope::~PhaseScope() {
 void collect_phase_times(Engine& e) {
     NB_CUDA(cudaStreamSynchronize(e.stream));
     for (int p = 0; p < NBX_NUM_PHASES; p++) {
-        double sum = 0.0;
+        double sum = 0.0, subsum[Engine::kPhaseSub] = {};
         int cnt = 0;
         for (int k = 0; k < e.ev_count[p]; k++) {
             bool any = false;
@@ -157,6 +157,7 @@ void collect_phase_times(Engine& e) {
                 float ms = 0.f;
                 if (e.ev[p][k][u][0] && cudaEventElapsedTime(&ms, e.ev[p][k][u][0], e.ev[p][k][u][1]) == cudaSuccess) {
                     sum += ms;
+                    subsum[u] += ms;
                     any = true;
                 }
                 (void)cudaGetLastError();
@@ -164,6 +165,7 @@ void collect_phase_times(Engine& e) {
             if (any) cnt++;
         }
         e.phase_ms[p] = cnt ? static_cast<float>(sum / cnt) : 0.f;
+        for (int u = 0; u < Engine::kPhaseSub; u++) e.phase_sub_ms[p][u] = cnt ? static_cast<float>(subsum[u] / cnt) : 0.f;
         e.ev_count[p] = 0;
         for (int k = 0; k < Engine::kPhaseRing; k++) e.ev_sub[p][k] = 0;
     }

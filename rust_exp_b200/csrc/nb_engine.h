@@ -125,6 +125,15 @@ struct AllPairsArgs {
     uint32_t wait_step;
     int my_rank;
     unsigned long long timeout_ns;   // bound on the cross-rank waits (0 = none)
+    // P2P_DIRECT, staged: the first 2*(nseg-1) CTAs first copy one half of one REMOTE segment each from the peer's
+    // HBM (src[]) into the local mirror, once per step, then join the work loop; every j tile is then streamed from
+    // local memory (seg[] points at the mirror for remote segments).  NVLink volume = the all-gather's, not x n_itiles.
+    int stage;                       // 0: seg[] are read in place (peer memory for remote segments)
+    JSeg src[kMaxRanks];             // where the stagers read segment g (peer arena)
+    JSeg dst[kMaxRanks];             // where they write it (local mirror) == seg[g] for remote g
+    int stage_mass;                  // masses are constant between set calls: staged on the first step only
+    uint32_t* staged;                // staged[g] += 1 per finished half
+    uint32_t stage_want;             // producers read segment g once staged[g] >= stage_want
 };
 
 struct Tuning {
@@ -176,6 +185,8 @@ struct Engine {
     float* mirror = nullptr;
     size_t mirror_cap = 0;
     bool mirror_mass_valid = false;  // masses are constant between set/generate calls: gathered once
+    uint32_t* stage_flags = nullptr; // [kMaxRanks] halves staged per remote segment (P2P_DIRECT staged)
+    uint32_t stage_epoch = 0;
     // scratch
     float2* partial = nullptr;
     size_t partial_cap = 0;  // in float2
@@ -198,6 +209,7 @@ struct Engine {
     int ev_count[NBX_NUM_PHASES] = {};
     int ev_slot = 0;  // step index within the ring
     float phase_ms[NBX_NUM_PHASES] = {};
+    float phase_sub_ms[NBX_NUM_PHASES][4] = {};   // the same, per sub-interval of a step (entry order)
 
     // Barnes-Hut workspace, opaque (nb_bh.cu)
     void* bh = nullptr;
