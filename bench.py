@@ -501,6 +501,7 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
             allr = [None] * world
             cx.dist.all_gather_object(allr, mine)
             out["per_rank"] = allr
+            out["ordering_point_ms"] = cx.allreduce([lib.dist_sync_test(200)], "max")[0]   # floor of one of the 4 per-step syncs
     out["e2e"] = {"value": e2e_value, "unit": out["unit"], "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                   "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "what": e2e_what}
     if w["kind"] == "bh":
@@ -646,7 +647,7 @@ def main():
     }
     for k in ("fp32_tflops", "fp32_frac_of_peak_all_gpus", "roofline_hbm", "steps_per_s", "interactions_per_s", "lane_efficiency",
               "lanes_per_pop_histogram", "pops_per_step", "interactions_per_step", "nodes_visited_per_step", "tree_nodes",
-              "walk_imbalance_max_over_mean", "cpu_baseline", "per_rank", "sort_levels"):
+              "walk_imbalance_max_over_mean", "cpu_baseline", "per_rank", "sort_levels", "ordering_point_ms"):
         if k in m:
             line[k] = m[k]
     if w["kind"] == "bh":

@@ -228,6 +228,9 @@ int32_t nbx_dist_set_transport(int32_t transport);
  * (initial-condition loading, rank-0-only I/O), short enough that a dead peer does not hang the GPU. */
 int32_t nbx_set_peer_timeout_ms(int32_t ms);
 int32_t nbx_dist_local_range(int32_t *begin, int32_t *count);
+/* Diagnostic (collective): average device time in ms of one cross-rank ordering point -- a 32-thread kernel that stores
+ * an epoch flag into every peer's arena and waits for every peer's -- over `iters` back-to-back launches. */
+float nbx_dist_sync_test(int32_t iters);
 /* Owner-only read-back: fills rows [begin, begin+count) (this rank's shard, see nbx_dist_local_range) of the
  * caller's FULL n-row AoS array and leaves the other rows untouched -- count*20 bytes of device->host traffic
  * instead of n*20 on every rank.  Not a collective.  On one GPU it equals nb_get_particles. */

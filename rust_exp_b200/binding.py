@@ -75,6 +75,7 @@ SYMBOLS = {
     "nbx_dist_nccl_init": (i32, [vp]),
     "nbx_dist_set_transport": (i32, [i32]),
     "nbx_dist_local_range": (i32, [vp, vp]),
+    "nbx_dist_sync_test": (f32, [i32]),
     "nbx_get_particles_local": (i32, [vp, i32]),
 }
 
@@ -310,6 +311,9 @@ class NBodyLib:
 
     def dist_set_transport(self, t: int) -> None:
         self._chk(self.L.nbx_dist_set_transport(t), "nbx_dist_set_transport")
+
+    def dist_sync_test(self, iters: int = 200) -> float:
+        return float(self.L.nbx_dist_sync_test(iters))
 
     def dist_local_range(self) -> tuple[int, int]:
         b, c = i32(0), i32(0)

@@ -454,6 +454,12 @@ int32_t nbx_dist_set_transport(int32_t transport) {
     engine().transport = transport;
     return 0;
 }
+float nbx_dist_sync_test(int32_t iters) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    return bh_sync_test(e, iters);
+}
 int32_t nbx_dist_local_range(int32_t* begin, int32_t* count) {
     NB_LOCK();
     Engine& e = engine();

@@ -203,6 +203,7 @@ struct BhWork {
     std::vector<PartBufs> parts;
     TopBufs top;
     uint32_t bh_epoch = 0;
+    uint32_t sync_test_epoch = 0;
     float2* acc_src = nullptr;       // where this step's per-local-body accelerations ended up
     TreeTable last_tt{};             // the tree of the most recent FAST step (for nbx_bh_flatten)
     int last_nparts = 0;             // 0 = no FAST tree yet, 1 = single tree, >1 = partitioned
@@ -1601,7 +1602,7 @@ struct MergeArgs {
     size_t stride;
     BhStatus* st;
 };
-constexpr int kMergeSamples = 512;   // per run: every S-th key cached in shared memory (S = power of two, sized per step)
+constexpr int kMergeSamples = 256;   // per run: every S-th key cached in shared memory (S = power of two, sized per step)
 __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
     __shared__ int cnt[kMaxRanks], off[kMaxRanks + 1];
     __shared__ int s_shift;
@@ -1753,18 +1754,38 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
         a.tchild[offk + c] = en.child;
         wts[c] = kBodyWeight * static_cast<unsigned long long>(en.count) + a.work[c];
     }
+    __shared__ unsigned long long warp_tot[8];
+    __shared__ int s_cut[kMaxRanks + 1];
     if (tid == 0) s_top = 0;
+    if (tid <= kMaxRanks) s_cut[tid] = kNumCells;
     __syncthreads();
-    if (tid == 32) {   // a second warp: the next partition, while warp 0 goes on with the tree
-        unsigned long long total = 0, cum = 0;
-        for (int c = 0; c < kNumCells; c++) total += wts[c];
-        int g = 1;
-        a.plan_next->cut[0] = 0;
-        for (int c = 0; c < kNumCells; c++) {
-            while (g < a.nparts && cum * a.nparts >= static_cast<unsigned long long>(g) * total) a.plan_next->cut[g++] = c;
-            cum += wts[c];
+    {   // the next partition: block-wide exclusive prefix of the cell weights (thread t owns cells 4t..4t+3), then every
+        // cell whose prefix reaches g/G of the total bids for cut g; the lowest bidder is the cut
+        static_assert(kNumCells == 4 * 256, "one thread per four cells");
+        const unsigned long long w0 = wts[4 * tid], w1 = wts[4 * tid + 1], w2 = wts[4 * tid + 2], w3 = wts[4 * tid + 3];
+        unsigned long long inc = w0 + w1 + w2 + w3;
+        const int ln = tid & 31, wp = tid >> 5;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (ln >= o) inc += v;
         }
-        while (g <= a.nparts) a.plan_next->cut[g++] = kNumCells;
+        if (ln == 31) warp_tot[wp] = inc;
+        __syncthreads();
+        unsigned long long base = 0, total = 0;
+        for (int k = 0; k < 8; k++) { if (k < wp) base += warp_tot[k]; total += warp_tot[k]; }
+        const unsigned long long e0 = base + inc - (w0 + w1 + w2 + w3), e1 = e0 + w0, e2 = e1 + w1, e3 = e2 + w2;
+        const unsigned long long G = static_cast<unsigned long long>(a.nparts);
+        for (int g = 1; g < a.nparts; g++) {
+            const unsigned long long target = static_cast<unsigned long long>(g) * total;
+            int c = kNumCells;
+            if (e3 * G >= target) c = 4 * tid + 3;
+            if (e2 * G >= target) c = 4 * tid + 2;
+            if (e1 * G >= target) c = 4 * tid + 1;
+            if (e0 * G >= target) c = 4 * tid;
+            if (c < kNumCells) atomicMin(&s_cut[g], c);
+        }
+        __syncthreads();
+        if (tid <= a.nparts) a.plan_next->cut[tid] = tid == 0 ? 0 : (tid == a.nparts ? kNumCells : s_cut[tid]);
     }
     for (int l = kCutLevel - 1; l >= 0; l--) {
         const int off = top_off_level(l), offc = top_off_level(l + 1);
@@ -2038,7 +2059,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             PartBufs& P = w.parts[r];
             const size_t stride = P.cap + 1;
             MergeArgs ma{P.arena, lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R, nparts, P.mkeys, P.sx, P.sy, P.sm, P.gidx, P.w3, stride, P.status};
-            bhp_merge_kernel<<<std::min(GE, e.num_sms * 4), T, 0, s>>>(ma);
+            bhp_merge_kernel<<<std::min(GE, e.num_sms * 2), T, 0, s>>>(ma);
             launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride, e.num_sms * 4);
             e.ctr.kernel_launches += 4;
         }
@@ -2193,6 +2214,29 @@ void bh_pop_histogram(Engine& e, uint64_t* out33, bool reset) {
     check_status(e, w, true);
     for (int k = 0; k < 33; k++) { out33[k] = w.pop_hist[k]; if (reset) w.pop_hist[k] = 0; }
 }
+// Diagnostic: `iters` back-to-back ordering points (signal + wait, one launch each) on a private flag row, timed with
+// events -- the floor the four per-step ordering points of the partitioned step cannot go below.
+float bh_sync_test(Engine& e, int iters) {
+    if (!(e.dist && e.world > 1) || !e.bh_arena || iters <= 0) return 0.f;
+    dist_require_peers(e);
+    BhWork& w = work(e);
+    PeerArenas peers{};
+    for (int g = 0; g < e.world; g++) peers.a[g] = e.bh_peer[g];
+    cudaEvent_t a, b;
+    NB_CUDA(cudaEventCreate(&a)); NB_CUDA(cudaEventCreate(&b));
+    for (int k = 0; k < 4; k++)
+        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, ++w.sync_test_epoch, e.peer_timeout_ns);
+    NB_CUDA(cudaEventRecord(a, e.stream));
+    for (int k = 0; k < iters; k++)
+        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, ++w.sync_test_epoch, e.peer_timeout_ns);
+    NB_CUDA(cudaEventRecord(b, e.stream));
+    NB_CUDA(cudaStreamSynchronize(e.stream));
+    float ms = 0.f;
+    NB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ms / iters;
+}
+
 void bh_poll(Engine& e) {
     if (e.bh) check_status(e, work(e), true);
 }

@@ -57,7 +57,7 @@ struct ArenaLayout {
 //   acc[L_cap]          accelerations of the bodies this rank owns by index, scattered here by whoever walked them
 constexpr int kBhCutLevel = 5;
 constexpr int kBhNumCells = 1 << (2 * kBhCutLevel);   // 1024 cells at the cut level
-constexpr int kBhFlagRows = 4;
+constexpr int kBhFlagRows = 5;   // boxes / bodies / trees / walks + one row for nbx_dist_sync_test
 struct BhArenaLayout {
     int world = 1;
     size_t R = 0;            // inbox region capacity (bodies) per source rank = shard capacity
@@ -277,6 +277,7 @@ void bh_accelerations(Engine& e, float theta, float2* out);
 void bh_shutdown(Engine& e);
 int bh_flatten(Engine& e, float* out9, int cap);   // FAST tree of the last BH call, oracle flatten format
 void bh_poll(Engine& e);
+float bh_sync_test(Engine& e, int iters);   // average ms of one cross-rank ordering point (diagnostic)
 void bh_pop_histogram(Engine& e, uint64_t* out33, bool reset);   // fold the last Barnes-Hut step's status/counters in (synchronises)
 
 // nb_3d.cu

@@ -55,26 +55,59 @@ class ShardLayout:
         return [(rank + q) % self.world for q in range(self.world)]
 
 
-def sfc_partition(cell_counts, nparts: int) -> list[int]:
-    """Cut points of the Barnes-Hut domain split (mirror of nb_bh.cu::bh_forces_partitioned).
+BODY_WEIGHT = 8  # nb_bh.cu kBodyWeight: build cost of one body in units of one walk pop
 
-    `cell_counts[c]` = bodies in level-5 quadtree cell c, cells in Morton order.  Part g owns the contiguous
-    cell range [cut[g], cut[g+1]); a cut is placed at the first cell whose exclusive prefix count reaches
-    g*N/nparts, so every part gets ~N/nparts bodies up to the granularity of one cell, every cell has
-    exactly one owner, and all ranks compute the same cuts from the same histogram."""
-    n = int(sum(cell_counts))
+
+def sfc_partition(cell_weights, nparts: int) -> list[int]:
+    """Cut points of the Barnes-Hut domain split (mirror of nb_bh.cu::bh_top_build_kernel).
+
+    `cell_weights[c]` = weight of cut-level quadtree cell c, cells in Morton order -- on the device
+    BODY_WEIGHT * bodies(c) + walk cost measured for c on the previous step (body counts alone on the first step).
+    Part g owns the contiguous cell range [cut[g], cut[g+1]); a cut is placed at the first cell whose exclusive
+    prefix weight reaches g*W/nparts, so every part gets ~W/nparts of the work up to the granularity of one cell,
+    every cell has exactly one owner, and all ranks compute the same cuts from the same table."""
+    total = int(sum(int(k) for k in cell_weights))
     cut = [0]
     cum = 0
     g = 1
-    for c, k in enumerate(cell_counts):
-        while g < nparts and cum * nparts >= g * n:
+    for c, k in enumerate(cell_weights):
+        while g < nparts and cum * nparts >= g * total:
             cut.append(c)
             g += 1
         cum += int(k)
     while g <= nparts:
-        cut.append(len(cell_counts))
+        cut.append(len(cell_weights))
         g += 1
     return cut
+
+
+def run_boundaries(sorted_cells, cut) -> list[int]:
+    """Mirror of nb_bh.cu::bhp_send_kernel: a shard sorted by key falls apart into len(cut)-1 contiguous runs, run p =
+    the bodies whose cut-level cell lies in [cut[p], cut[p+1]).  Returns the run starts (+ the end)."""
+    import bisect
+
+    return [bisect.bisect_left(sorted_cells, c) for c in cut]
+
+
+def merge_by_rank(runs):
+    """Mirror of nb_bh.cu::bhp_merge_kernel: G key-sorted runs -> one sorted sequence without any global sort.  Element
+    i of run s goes to position i + sum over the other runs r of (elements of r that are < key, or <= key when r < s):
+    ties are ordered by source rank, then by position, so the result is deterministic.  Returns (keys, (source, index))."""
+    import bisect
+
+    n = sum(len(r) for r in runs)
+    keys = [None] * n
+    origin = [None] * n
+    for s, run in enumerate(runs):
+        for i, k in enumerate(run):
+            pos = i
+            for r, other in enumerate(runs):
+                if r == s:
+                    continue
+                pos += bisect.bisect_right(other, k) if r < s else bisect.bisect_left(other, k)
+            keys[pos] = k
+            origin[pos] = (s, i)
+    return keys, origin
 
 
 def all_gather_bytes(payload: bytes, group=None) -> list[bytes]:

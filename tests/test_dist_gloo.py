@@ -16,7 +16,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from rust_exp_b200 import ic
-from rust_exp_b200.dist import ShardLayout, all_gather_bytes, broadcast_bytes, wire
+from rust_exp_b200.dist import (ShardLayout, all_gather_bytes, broadcast_bytes, merge_by_rank, run_boundaries, sfc_partition,
+                                wire)
 
 
 def _free_port():
@@ -128,3 +129,61 @@ PORT = [0]
 def _port():
     PORT[0] = _free_port()
     yield
+
+
+# ---- the Barnes-Hut exchange of the domain-partitioned step, host-side model over gloo -----------------------------
+def _bh_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        # 48-bit Morton-like keys with many ties in the top bits AND some fully identical keys
+        keys_all = (rng.integers(0, 1 << 14, n).astype(np.uint64) << np.uint64(34)) | rng.integers(0, 4, n).astype(np.uint64)
+        lay = ShardLayout.for_capacity(n, world).for_set(n)
+        b, c = lay.local_range(rank, n)
+        mine = keys_all[b:b + c]
+        order = np.argsort(mine, kind="stable")                   # the rank's own radix sort (stable)
+        ks = mine[order]
+        cells = (ks >> np.uint64(38)).astype(np.int64)            # cut-level cell = top 10 of 48 bits
+        # every rank derives the same partition from the same (all-reduced) cell histogram
+        hist = torch.from_numpy(np.bincount((keys_all[b:b + c] >> np.uint64(38)).astype(np.int64), minlength=1024))
+        dist.all_reduce(hist)
+        cut = sfc_partition(hist.tolist(), world)
+        lo = run_boundaries(cells.tolist(), cut)
+        runs_out = [[(int(ks[i]), b + int(order[i])) for i in range(lo[p], lo[p + 1])] for p in range(world)]
+        # the all-to-all-v: run p goes to rank p (NVLink peer stores on the device; object all-gather here)
+        box = [None] * world
+        dist.all_gather_object(box, runs_out)
+        inbox = [box[s][rank] for s in range(world)]              # what every source sent to ME, in source order
+        keys, origin = merge_by_rank([[k for k, _ in r] for r in inbox])
+        gidx = [inbox[s][i][1] for s, i in origin]
+        out = [None] * world
+        dist.all_gather_object(out, (keys, gidx, cut))
+        if rank == 0:
+            q.put((out, keys_all))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_exchange_equals_global_stable_sort():
+    """Shard-local sort -> runs by destination part -> exchange -> merge by ranking gives, part after part, exactly the
+    global stable sort by (key, global index): what one GPU's radix sort over all bodies would have produced."""
+    world, n = 2, 6000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bh_worker, args=(r, world, PORT[0], n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out, keys_all = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][2] == out[1][2]                                 # same cuts on every rank
+    merged_keys = [k for part in out for k in part[0]]
+    merged_idx = [g for part in out for g in part[1]]
+    ref = np.argsort(keys_all, kind="stable")
+    assert merged_keys == [int(k) for k in keys_all[ref]]
+    assert merged_idx == [int(i) for i in ref]
+    sizes = [len(part[0]) for part in out]
+    assert sum(sizes) == n and max(sizes) - min(sizes) <= n // 8   # cell-granular balance
