@@ -121,6 +121,7 @@ struct TopBufs {
     float4* blk = nullptr;        // top blocks: 1 + (kTopNodes - kNumCells) blocks
     int4* cblk = nullptr;
     PartPlan* plan = nullptr;     // [2]: plan[e & 1] is the partition step e uses; step e writes plan[(e + 1) & 1]
+    uint32_t* epoch_dev = nullptr; // the step counter e of the partitioned path (device-resident: graphs replay unchanged)
     bool plan_valid = false;
     int plan_n = -1, plan_parts = -1;
 };
@@ -196,6 +197,10 @@ struct BhWork {
         int sort_levels = 0;
         float kick = 0.f;
         int square = 0;
+        int nparts = 0;                  // 1 = single tree, > 1 = domain-partitioned step
+        bool partitioned = false;
+        float2* acc_src = nullptr;       // host-side results of the capture, restored on every replay
+        TreeTable tt{};
     } graph[2];
     uint64_t alloc_gen = 0;          // bumped whenever a buffer a captured graph points at is (re)allocated
     bool capturing = false;
@@ -810,8 +815,9 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
     float theta2, BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
-    unsigned* __restrict__ cell_work, const int* __restrict__ n_dev) {
+    unsigned* __restrict__ cell_work, const int* __restrict__ n_dev, const uint32_t* __restrict__ epoch_dev) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
+    if (cell_work != nullptr && epoch_dev != nullptr) cell_work += (*epoch_dev & 1u) * kNumCells;   // this step's parity
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lanebit = 1u << lane;
     if (n_dev) n_list = *n_dev;     // partitioned step: the size of the part's body list only exists on the device
@@ -1226,7 +1232,8 @@ static int traverse_resident_blocks(Engine& e) {
 // ticket_slot: which st->tickets[] counter this launch draws its groups from (one per launch between two resets)
 static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, const float* sy, const int* idx_sorted,
                             const int* mine, int n_list, float theta, BhStatus* st, int ticket_slot = 0,
-                            const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr, const int* n_dev = nullptr) {
+                            const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr, const int* n_dev = nullptr,
+                            const uint32_t* epoch_dev = nullptr) {
     // n_dev given: n_list is only an estimate for sizing the (persistent) grid
     const int want = std::max(1, (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32));
     const int blocks = std::min(want, traverse_resident_blocks(e));
@@ -1235,7 +1242,7 @@ static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, con
     // The sparse (octet) pass is an experiment that LOST (profiles/r02_walk_sparse_pass_ab.jsonl: 1.7x slower -- the
     // sub-warp collectives it needs compile to WARPSYNC/ENDCOLLECTIVE loops): off unless NB_BH_SPARSE=1.
     static const bool sparse = [] { const char* v = getenv("NB_BH_SPARSE"); return v ? atoi(v) != 0 : false; }();
-#define NB_TRAV(C, P, S) bh_traverse_fast_kernel<C, P, S><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev)
+#define NB_TRAV(C, P, S) bh_traverse_fast_kernel<C, P, S><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
 #define NB_TRAV2(C, P) do { if (sparse) NB_TRAV(C, P, true); else NB_TRAV(C, P, false); } while (0)
     if (e.bh_count) { if (parts) NB_TRAV2(true, true); else NB_TRAV2(true, false); }
     else { if (parts) NB_TRAV2(false, true); else NB_TRAV2(false, false); }
@@ -1500,7 +1507,19 @@ constexpr unsigned long long kBodyWeight = 8ull;   // build cost of one body in 
 
 struct PeerArenas { char* a[kMaxRanks]; };
 
-__global__ void bhp_signal_kernel(PeerArenas peers, size_t off_flags, int row, int world, int me, uint32_t epoch) {
+// The step counter of the partitioned path lives on the device (EpochRef.p), so that a captured CUDA graph of the whole
+// step replays unchanged: kernels read it, and select the step-parity buffers (partition plan, walk costs) themselves.
+struct EpochRef {
+    const uint32_t* p;   // device counter, or nullptr ...
+    uint32_t v;          // ... then this value
+    __device__ __forceinline__ uint32_t get() const { return p ? *p : v; }
+};
+__global__ void bhp_epoch_inc_kernel(uint32_t* epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *epoch += 1u;
+}
+
+__global__ void bhp_signal_kernel(PeerArenas peers, size_t off_flags, int row, int world, int me, EpochRef er) {
+    const uint32_t epoch = er.get();
     const int g = threadIdx.x;
     if (g < world) {
         __threadfence_system();
@@ -1508,15 +1527,17 @@ __global__ void bhp_signal_kernel(PeerArenas peers, size_t off_flags, int row, i
         __threadfence_system();
     }
 }
-__global__ void bhp_wait_kernel(const char* arena, size_t off_flags, int row, int world, uint32_t epoch, unsigned long long timeout_ns) {
+__global__ void bhp_wait_kernel(const char* arena, size_t off_flags, int row, int world, EpochRef er, unsigned long long timeout_ns) {
+    const uint32_t epoch = er.get();
     const int g = threadIdx.x;
     if (g < world)
         wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + row * 64 + g, epoch, timeout_ns, g, "Barnes-Hut epoch");
 }
 
 // signal + wait in one launch: thread g tells peer g "I reached `row` of this epoch", then waits for peer g's
-__global__ void bhp_sync_kernel(PeerArenas peers, const char* arena, size_t off_flags, int row, int world, int me, uint32_t epoch,
+__global__ void bhp_sync_kernel(PeerArenas peers, const char* arena, size_t off_flags, int row, int world, int me, EpochRef er,
                                 unsigned long long timeout_ns) {
+    const uint32_t epoch = er.get();
     const int g = threadIdx.x;
     if (g < world) {
         __threadfence_system();
@@ -1527,7 +1548,10 @@ __global__ void bhp_sync_kernel(PeerArenas peers, const char* arena, size_t off_
 
 // my local box -> slot `me` of every peer's box table, then the "boxes" flag
 __global__ void bhp_boxes_publish_kernel(const BhStatus* st, PeerArenas peers, size_t off_aabb, size_t off_flags, int world, int me,
-                                         uint32_t epoch) {
+                                         EpochRef er, unsigned* cellwork2) {
+    const uint32_t epoch = er.get();
+    // this step's walk-cost table (the parity nobody reads any more) starts from zero
+    for (int c = threadIdx.x; c < kNumCells; c += blockDim.x) cellwork2[(epoch & 1u) * kNumCells + c] = 0u;
     const int g = threadIdx.x;
     if (g < world) {
         volatile int* dst = reinterpret_cast<volatile int*>(peers.a[g] + off_aabb) + 4 * me;
@@ -1538,8 +1562,9 @@ __global__ void bhp_boxes_publish_kernel(const BhStatus* st, PeerArenas peers, s
     }
 }
 // wait for all G boxes, reduce (exact), store the global box where the key / build / top kernels read it
-__global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size_t off_flags, int world, uint32_t epoch,
+__global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size_t off_flags, int world, EpochRef er,
                                         unsigned long long timeout_ns, BhStatus* st_part, BhStatus* st_global, int square) {
+    const uint32_t epoch = er.get();
     const int g = threadIdx.x;
     if (g < world)
         wait_epoch(reinterpret_cast<const uint32_t*>(arena + off_flags) + kFlagBoxes * 64 + g, epoch, timeout_ns, g, "Barnes-Hut boxes");
@@ -1563,7 +1588,8 @@ struct SendArgs {
     const int* order;
     const float *x, *y, *m;
     int n_local, gbegin;
-    const PartPlan* plan;
+    const PartPlan* plan2;      // [2]; this step's is plan2[epoch & 1]
+    EpochRef er;
     int nparts, me;
     PeerArenas peers;
     size_t off_in_key, off_in_rec, off_count_in, R;
@@ -1572,7 +1598,8 @@ __global__ void __launch_bounds__(256) bhp_send_kernel(const SendArgs a) {
     __shared__ int lo[kMaxRanks + 1];
     if (threadIdx.x <= a.nparts) {
         // first sorted body whose cut-level cell is >= cut[p]: the start of part p's run
-        const unsigned long long kmin = static_cast<unsigned long long>(a.plan->cut[threadIdx.x]) << kCellShift;
+        const PartPlan* plan = a.plan2 + (a.er.get() & 1u);
+        const unsigned long long kmin = static_cast<unsigned long long>(plan->cut[threadIdx.x]) << kCellShift;
         int l = 0, h = a.n_local;
         while (l < h) { const int mid = (l + h) >> 1; if (a.keys[a.order[mid]] < kmin) l = mid + 1; else h = mid; }
         lo[threadIdx.x] = l;
@@ -1667,19 +1694,22 @@ struct PubArgs {
     PeerArenas peers;
     size_t off_celltab, off_workpub;
     int nparts;
-    const PartPlan* plan;        // this step's partition
-    const PartPlan* plan_prev;   // last step's (the buffer the top build will overwrite with the next one)
+    const PartPlan* plan2;       // [2]: this step's partition is plan2[epoch & 1]; the other one still holds last step's
+    EpochRef er;
     int part;
-    const unsigned* work_prev;   // this rank's measured walk cost per cell, last step
+    const unsigned* cellwork2;   // [2][cells]: this rank's measured walk cost per cell; last step's is parity (epoch + 1) & 1
 };
 __global__ void bh_celltab_kernel(const BuildArgs a, const PubArgs pub) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= kNumCells) return;
-    if (c >= pub.plan_prev->cut[pub.part] && c < pub.plan_prev->cut[pub.part + 1]) {
-        const unsigned wk = pub.work_prev[c];
+    const uint32_t epoch = pub.er.get();
+    const PartPlan* plan = pub.plan2 + (epoch & 1u);
+    const PartPlan* plan_prev = pub.plan2 + ((epoch + 1u) & 1u);
+    if (c >= plan_prev->cut[pub.part] && c < plan_prev->cut[pub.part + 1]) {
+        const unsigned wk = pub.cellwork2[((epoch + 1u) & 1u) * kNumCells + c];
         for (int g = 0; g < pub.nparts; g++) reinterpret_cast<unsigned*>(pub.peers.a[g] + pub.off_workpub)[c] = wk;
     }
-    if (c < pub.plan->cut[pub.part] || c >= pub.plan->cut[pub.part + 1]) return;
+    if (c < plan->cut[pub.part] || c >= plan->cut[pub.part + 1]) return;
     const int n = build_n(a);
     const size_t stride = a.stride;
     auto lb = [&](unsigned long long cell) {   // first sorted body whose cell index is >= cell
@@ -1718,8 +1748,8 @@ __global__ void bh_celltab_kernel(const BuildArgs a, const PubArgs pub) {
 struct TopArgs {
     const CellEntry* tab;              // the complete cell table (local copy, filled by all ranks)
     const unsigned* work;              // work[c] = walk cost measured for cell c on the previous step (local copy)
-    const PartPlan* plan;              // this step's partition
-    PartPlan* plan_next;               // next step's, computed here from the same data on every rank
+    PartPlan* plan2;                   // [2]: plan2[(epoch + 1) & 1] receives the NEXT step's partition, computed here
+    EpochRef er;
     int nparts;
     int* tcount; double* tm3; float4* tleaf; int* tchild;
     float4* blk; int4* cblk;
@@ -1785,7 +1815,8 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
             if (c < kNumCells) atomicMin(&s_cut[g], c);
         }
         __syncthreads();
-        if (tid <= a.nparts) a.plan_next->cut[tid] = tid == 0 ? 0 : (tid == a.nparts ? kNumCells : s_cut[tid]);
+        PartPlan* plan_next = a.plan2 + ((a.er.get() + 1u) & 1u);
+        if (tid <= a.nparts) plan_next->cut[tid] = tid == 0 ? 0 : (tid == a.nparts ? kNumCells : s_cut[tid]);
     }
     for (int l = kCutLevel - 1; l >= 0; l--) {
         const int off = top_off_level(l), offc = top_off_level(l + 1);
@@ -1928,45 +1959,73 @@ static void top_ensure(TopBufs& t) {
     NB_CUDA(cudaMalloc(&t.blk, sizeof(float4) * 4 * (kTopNodes + 1)));
     NB_CUDA(cudaMalloc(&t.cblk, sizeof(int4) * (kTopNodes + 1)));
     NB_CUDA(cudaMalloc(&t.plan, sizeof(PartPlan) * 2));
+    NB_CUDA(cudaMalloc(&t.epoch_dev, sizeof(uint32_t)));
+    NB_CUDA(cudaMemset(t.epoch_dev, 0, sizeof(uint32_t)));
+}
+
+// geometry of the parts this process runs (real ranks: one; virtual ranks: all nparts)
+struct PartGeom {
+    bool real;
+    int nlocal;
+    size_t shard;          // index-shard length: owner of body i is i / shard
+    BhArenaLayout lay;
+};
+static PartGeom part_geometry(const Engine& e, int nparts) {
+    PartGeom g;
+    g.real = e.dist && e.world > 1;
+    g.nlocal = g.real ? 1 : nparts;
+    g.shard = e.lay.L;
+    if (g.real) {
+        g.lay = e.bh_lay;
+    } else {
+        g.shard = ((static_cast<size_t>(e.n) + nparts - 1) / nparts + kShardAlign - 1) / kShardAlign * kShardAlign;
+        g.lay.set(g.shard, nparts, static_cast<size_t>(e.n));   // virtual ranks: a private layout sized for this set
+    }
+    return g;
+}
+
+// everything of the partitioned step that allocates, synchronises or bootstraps: must run OUTSIDE a graph capture
+static void bh_prepare_partitioned(Engine& e, int nparts) {
+    BhWork& w = work(e);
+    cudaStream_t s = e.stream;
+    const PartGeom pg = part_geometry(e, nparts);
+    top_ensure(w.top);
+    if (static_cast<int>(w.parts.size()) != pg.nlocal) {
+        NB_CUDA(cudaStreamSynchronize(s));
+        for (PartBufs& P : w.parts) part_free(P);
+        w.parts.assign(pg.nlocal, PartBufs());
+    }
+    for (int r = 0; r < pg.nlocal; r++)
+        part_ensure(e, w, w.parts[r], static_cast<int>(pg.real ? e.L_cap : pg.shard),
+                    pg.real ? static_cast<size_t>(e.max_particles) : static_cast<size_t>(e.n), pg.lay, pg.real ? e.bh_arena : nullptr);
+    if (pg.real) dist_require_peers(e);
+    if (!w.top.plan_valid || w.top.plan_n != e.n || w.top.plan_parts != nparts) {
+        bhp_plan_init_kernel<<<1, 32, 0, s>>>(w.top.plan, nparts);   // bootstrap: equal cell ranges; balanced from the next step on
+        w.top.plan_valid = true; w.top.plan_n = e.n; w.top.plan_parts = nparts;
+        for (int r = 0; r < pg.nlocal; r++)
+            NB_CUDA(cudaMemsetAsync(w.parts[r].arena + pg.lay.off_cellwork, 0, 2 * kNumCells * sizeof(unsigned), s));
+        e.ctr.kernel_launches++;
+    }
 }
 
 static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     BhWork& w = work(e);
-    const bool real = e.dist && e.world > 1;      // real ranks: this process is part e.rank only
-    const int n = e.n;
+    if (!w.capturing) bh_prepare_partitioned(e, nparts);
+    const PartGeom pg = part_geometry(e, nparts);
+    const bool real = pg.real;
+    const int n = e.n, nlocal = pg.nlocal;
+    const size_t shard = pg.shard;
+    const BhArenaLayout& lay = pg.lay;
     cudaStream_t s = e.stream;
     const int T = 256;
-    top_ensure(w.top);
-    // ---- geometry of the parts this process runs ----------------------------------------------------------------
-    const int nlocal = real ? 1 : nparts;
-    BhArenaLayout vlay;                              // virtual ranks: a private layout sized for this set
-    size_t shard = e.lay.L;                          // index-shard length: owner of body i is i / shard
-    if (!real) {
-        shard = ((static_cast<size_t>(n) + nparts - 1) / nparts + kShardAlign - 1) / kShardAlign * kShardAlign;
-        vlay.set(shard, nparts, static_cast<size_t>(n));
-    }
-    const BhArenaLayout& lay = real ? e.bh_lay : vlay;
-    if (static_cast<int>(w.parts.size()) != nlocal) {
-        NB_CUDA(cudaStreamSynchronize(s));
-        for (PartBufs& P : w.parts) part_free(P);
-        w.parts.assign(nlocal, PartBufs());
-    }
-    for (int r = 0; r < nlocal; r++)
-        part_ensure(e, w, w.parts[r], static_cast<int>(real ? e.L_cap : shard), real ? static_cast<size_t>(e.max_particles) : static_cast<size_t>(n),
-                    lay, real ? e.bh_arena : nullptr);
     PeerArenas peers{};
     for (int g = 0; g < nparts; g++) peers.a[g] = real ? e.bh_peer[g] : w.parts[g].arena;
-    if (real) dist_require_peers(e);
-    if (!w.top.plan_valid || w.top.plan_n != n || w.top.plan_parts != nparts) {
-        bhp_plan_init_kernel<<<1, 32, 0, s>>>(w.top.plan, nparts);   // bootstrap: equal cell ranges; balanced from the next step on
-        w.top.plan_valid = true; w.top.plan_n = n; w.top.plan_parts = nparts;
-        for (int r = 0; r < nlocal; r++)
-            NB_CUDA(cudaMemsetAsync(w.parts[r].arena + lay.off_cellwork, 0, 2 * kNumCells * sizeof(unsigned), s));
-        e.ctr.kernel_launches++;
-    }
-    const uint32_t epoch = ++w.bh_epoch;
-    const PartPlan* plan = w.top.plan + (epoch & 1u);
-    PartPlan* plan_next = w.top.plan + ((epoch + 1u) & 1u);
+    // the step counter advances on the device (a captured graph replays this launch); the host keeps a mirror
+    bhp_epoch_inc_kernel<<<1, 32, 0, s>>>(w.top.epoch_dev);
+    e.ctr.kernel_launches++;
+    ++w.bh_epoch;
+    const EpochRef er{w.top.epoch_dev, 0u};
+    PartPlan* plan2 = w.top.plan;
     auto part_id = [&](int r) { return real ? e.rank : r; };
     auto src_begin = [&](int r) { return real ? local_begin(e) : static_cast<int>(std::min<size_t>(static_cast<size_t>(r) * shard, static_cast<size_t>(n))); };
     auto src_count = [&](int r) {
@@ -1980,11 +2039,11 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
     // a cross-rank ordering point: real ranks signal + wait in one launch; virtual ranks (one stream) signal all, then wait
     auto sync_point = [&](int row) {
         if (real) {
-            bhp_sync_kernel<<<1, 32, 0, s>>>(peers, w.parts[0].arena, lay.off_flags, row, nparts, e.rank, epoch, e.peer_timeout_ns);
+            bhp_sync_kernel<<<1, 32, 0, s>>>(peers, w.parts[0].arena, lay.off_flags, row, nparts, e.rank, er, e.peer_timeout_ns);
             e.ctr.kernel_launches++;
         } else {
-            for (int r = 0; r < nlocal; r++) bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, row, nparts, r, epoch);
-            for (int r = 0; r < nlocal; r++) bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, row, nparts, epoch, e.peer_timeout_ns);
+            for (int r = 0; r < nlocal; r++) bhp_signal_kernel<<<1, 32, 0, s>>>(peers, lay.off_flags, row, nparts, r, er);
+            for (int r = 0; r < nlocal; r++) bhp_wait_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_flags, row, nparts, er, e.peer_timeout_ns);
             e.ctr.kernel_launches += 2 * nlocal;
         }
     };
@@ -1998,15 +2057,15 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             const int nl = src_count(r);
             bh_reset_kernel<<<1, 32, 0, s>>>(P.status);
             if (nl > 0) bh_aabb_kernel<<<std::min((nl + T - 1) / T, e.num_sms * 4), T, 0, s>>>(src_x(r), src_y(r), nl, P.status);
-            NB_CUDA(cudaMemsetAsync(P.arena + lay.off_cellwork + (epoch & 1u) * kNumCells * sizeof(unsigned), 0, kNumCells * sizeof(unsigned), s));
-            bhp_boxes_publish_kernel<<<1, 32, 0, s>>>(P.status, peers, lay.off_aabb, lay.off_flags, nparts, part_id(r), epoch);
+            bhp_boxes_publish_kernel<<<1, 32, 0, s>>>(P.status, peers, lay.off_aabb, lay.off_flags, nparts, part_id(r), er,
+                                                      reinterpret_cast<unsigned*>(P.arena + lay.off_cellwork));
             e.ctr.kernel_launches += 3;
         }
     }
     {
         PhaseScope ps(e, 7);
         for (int r = 0; r < nlocal; r++) {
-            bhp_boxes_reduce_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_aabb, lay.off_flags, nparts, epoch, e.peer_timeout_ns,
+            bhp_boxes_reduce_kernel<<<1, 32, 0, s>>>(w.parts[r].arena, lay.off_aabb, lay.off_flags, nparts, er, e.peer_timeout_ns,
                                                      w.parts[r].status, w.status, e.square_aabb);
             e.ctr.kernel_launches++;
         }
@@ -2043,7 +2102,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
             const int nl = src_count(r);
-            SendArgs sa{P.keys, order[r], src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan, nparts, part_id(r), peers,
+            SendArgs sa{P.keys, order[r], src_x(r), src_y(r), src_m(r), nl, src_begin(r), plan2, er, nparts, part_id(r), peers,
                         lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R};
             bhp_send_kernel<<<std::max(1, std::min((nl + T - 1) / T, e.num_sms * 8)), T, 0, s>>>(sa);
             e.ctr.kernel_launches++;
@@ -2078,8 +2137,8 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
                          static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, 1, nd, P.cap + 1};
             bh_owner_kernel<<<GE, T, 0, s>>>(ba, P.owner, P.status);
             bh_emit_kernel<<<std::min(GE, e.num_sms * 8), T, 0, s>>>(ba, P.owner, P.status);
-            PubArgs pa{peers, lay.off_celltab, lay.off_workpub, nparts, plan, plan_next, part_id(r),
-                       reinterpret_cast<const unsigned*>(P.arena + lay.off_cellwork) + ((epoch + 1u) & 1u) * kNumCells};
+            PubArgs pa{peers, lay.off_celltab, lay.off_workpub, nparts, plan2, er, part_id(r),
+                       reinterpret_cast<const unsigned*>(P.arena + lay.off_cellwork)};
             bh_celltab_kernel<<<(kNumCells + 127) / 128, 128, 0, s>>>(ba, pa);
             e.ctr.kernel_launches += 8;
         }
@@ -2103,7 +2162,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         }
         ta.tab = reinterpret_cast<const CellEntry*>(w.parts[0].arena + lay.off_celltab);      // every local part holds a complete copy
         ta.work = reinterpret_cast<const unsigned*>(w.parts[0].arena + lay.off_workpub);
-        ta.plan = plan; ta.plan_next = plan_next; ta.nparts = nparts;
+        ta.plan2 = plan2; ta.er = er; ta.nparts = nparts;
         ta.tcount = w.top.tcount; ta.tm3 = w.top.tm3; ta.tleaf = w.top.tleaf; ta.tchild = w.top.tchild;
         ta.blk = w.top.blk; ta.cblk = w.top.cblk;
         ta.top_off = static_cast<unsigned>(kMaxRanks) << kPartShift;
@@ -2117,7 +2176,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
             launch_traverse(e, tt, P.sx, P.sy, P.gidx, nullptr, est, theta, w.status, real ? 0 : r, P.mkeys,
-                            reinterpret_cast<unsigned*>(P.arena + lay.off_cellwork) + (epoch & 1u) * kNumCells, &P.status->n_part);
+                            reinterpret_cast<unsigned*>(P.arena + lay.off_cellwork), &P.status->n_part, w.top.epoch_dev);
         }
     }
     {
@@ -2225,10 +2284,10 @@ float bh_sync_test(Engine& e, int iters) {
     cudaEvent_t a, b;
     NB_CUDA(cudaEventCreate(&a)); NB_CUDA(cudaEventCreate(&b));
     for (int k = 0; k < 4; k++)
-        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, ++w.sync_test_epoch, e.peer_timeout_ns);
+        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, EpochRef{nullptr, ++w.sync_test_epoch}, e.peer_timeout_ns);
     NB_CUDA(cudaEventRecord(a, e.stream));
     for (int k = 0; k < iters; k++)
-        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, ++w.sync_test_epoch, e.peer_timeout_ns);
+        bhp_sync_kernel<<<1, 32, 0, e.stream>>>(peers, e.bh_arena, e.bh_lay.off_flags, 4, e.world, e.rank, EpochRef{nullptr, ++w.sync_test_epoch}, e.peer_timeout_ns);
     NB_CUDA(cudaEventRecord(b, e.stream));
     NB_CUDA(cudaStreamSynchronize(e.stream));
     float ms = 0.f;
@@ -2251,8 +2310,10 @@ static void bh_step_body(Engine& e, BhWork& w, float theta, float dt) {
 // The single-GPU FAST step is a fixed sequence of ~20 short kernels whose launch configuration depends only on
 // n: capture it once per position-buffer parity and replay it (NB_BH_GRAPH=0 disables).
 static bool bh_graph_eligible(const Engine& e) {
-    if (e.mode != NBX_MODE_FAST || e.phase_timing || e.bh_count || (e.dist && e.world > 1)) return false;
-    if (bh_partition_count(e) > 1) return false;
+    if (e.mode != NBX_MODE_FAST || e.phase_timing || e.bh_count) return false;
+    // sharded with ONE replicated tree: the position gather carries epoch values as launch parameters -> no replay.
+    // The domain-partitioned step (real or virtual ranks) keeps its step counter on the device and replays as a graph.
+    if (e.dist && e.world > 1 && bh_partition_count(e) == 1) return false;
     if (const char* s = getenv("NB_BH_GRAPH")) return atoi(s) != 0;
     return true;
 }
@@ -2272,9 +2333,11 @@ void bh_step(Engine& e, float theta, float dt) {
             w.cap_acc = static_cast<int>(e.lay.L);
             w.alloc_gen++;
         }
+        const int nparts_now = bh_partition_count(e);
+        if (nparts_now > 1) bh_prepare_partitioned(e, nparts_now);   // allocations / bootstrap never happen inside a capture
         BhWork::GraphSlot& g = w.graph[e.cur];
         // every pointer and scalar a captured launch carries is a function of this key (alloc_gen covers the workspace)
-        const bool hit = g.exec && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
+        const bool hit = g.exec && g.nparts == nparts_now && g.n == e.n && g.cur == e.cur && g.theta == theta && g.dt == dt && g.stream == e.stream &&
                          g.arena == e.arena.base && g.alloc_gen == w.alloc_gen && g.L == e.lay.L && g.sort_levels == w.sort_levels &&
                          g.kick == kick_dt(e, dt) && g.square == e.square_aabb;
         if (!hit) {
@@ -2301,22 +2364,23 @@ void bh_step(Engine& e, float theta, float dt) {
             NB_CUDA(cudaGraphDestroy(graph));
             g.n = e.n; g.cur = cur0; g.theta = theta; g.dt = dt; g.stream = e.stream; g.arena = e.arena.base;
             g.alloc_gen = w.alloc_gen; g.L = e.lay.L; g.sort_levels = w.sort_levels; g.kick = kick0; g.square = e.square_aabb;
+            g.nparts = nparts_now; g.partitioned = w.last_partitioned; g.acc_src = w.acc_src; g.tt = w.last_tt;
             g.launches = e.ctr.kernel_launches - l0;
             // the capture already advanced the host-side state exactly like a replay does below
         } else {
             e.ctr.kernel_launches += g.launches;
             e.cur ^= 1;
             if (e.integrator == NBX_INTEGRATOR_LEAPFROG_KDK) e.kdk_pending = 0.5f * dt;
-            w.acc_src = w.acc;
-            w.last_partitioned = false;
-            TreeTable tt{};
-            tt.blk[0] = w.nblk; tt.cblk[0] = w.ncblk; tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
-            w.last_tt = tt; w.last_nparts = 1;
+            w.acc_src = g.acc_src;
+            w.last_partitioned = g.partitioned;
+            w.last_tt = g.tt; w.last_nparts = g.nparts;
+            if (g.partitioned) { ++w.bh_epoch; w.last_nparts_hint = g.nparts; }   // mirrors of what the replayed launches do on the device
         }
         NB_CUDA(cudaGraphLaunch(g.exec, e.stream));
         BhWork::StatusSlot& sl = w.slot[w.cur_slot];   // the graph's last node copied the status block into this slot
         NB_CUDA(cudaEventRecord(sl.ev, e.stream));
-        sl.pending = true; sl.partitioned = false; sl.n = e.n;
+        sl.pending = true; sl.partitioned = g.partitioned;
+        sl.n = (g.partitioned && e.dist && e.world > 1) ? e.n / std::max(1, g.nparts) : e.n;
     } else {
         bh_step_body(e, w, theta, dt);
     }
@@ -2413,7 +2477,7 @@ void bh_shutdown(Engine& e) {
     }
     for (auto& g : w.graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (PartBufs& P : w.parts) part_free(P);
-    fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.plan);
+    fr(w.top.tcount); fr(w.top.tm3); fr(w.top.tleaf); fr(w.top.tchild); fr(w.top.blk); fr(w.top.cblk); fr(w.top.plan); fr(w.top.epoch_dev);
     delete &w;
     e.bh = nullptr;
 }
