@@ -1629,61 +1629,76 @@ struct MergeArgs {
     size_t stride;
     BhStatus* st;
 };
-constexpr int kMergeSamples = 256;   // per run: every S-th key cached in shared memory (S = power of two, sized per step)
+// Tile of 256 consecutive inbox elements (run-major order).  The keys of a tile span [kmin, kmax]; in every run r the
+// ranks of all the tile's keys lie inside the window [#keys < kmin, #keys <= kmax], found once per tile by 2 binary
+// searches per run -- so the per-element searches run over a few hundred keys that sit in L1, not over the whole run.
 __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
-    __shared__ int cnt[kMaxRanks], off[kMaxRanks + 1];
-    __shared__ int s_shift;
-    __shared__ unsigned long long samp[kMaxRanks][kMergeSamples];
+    __shared__ int cnt[kMaxRanks], off[kMaxRanks + 1], wlo[kMaxRanks], whi[kMaxRanks];
+    __shared__ unsigned long long rmin[kMaxRanks], rmax[kMaxRanks];
     const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(a.arena + a.off_in_key);
     const float4* recs = reinterpret_cast<const float4*>(a.arena + a.off_in_rec);
     if (threadIdx.x == 0) {
         const int* ci = reinterpret_cast<const int*>(a.arena + a.off_count_in);
-        int o = 0, mx = 0;
-        for (int s = 0; s < a.nparts; s++) { cnt[s] = ci[s]; off[s] = o; o += cnt[s]; mx = max(mx, cnt[s]); }
+        int o = 0;
+        for (int s = 0; s < a.nparts; s++) { cnt[s] = ci[s]; off[s] = o; o += cnt[s]; }
         off[a.nparts] = o;
-        int sh = 0;
-        while (((mx + (1 << sh) - 1) >> sh) > kMergeSamples) sh++;
-        s_shift = sh;
-        if (blockIdx.x == 0) a.st->n_part = o;
-    }
-    __syncthreads();
-    const int n = off[a.nparts], sh = s_shift, S = 1 << sh;
-    for (int r = 0; r < a.nparts; r++) {
-        const int ns = (cnt[r] + S - 1) >> sh;
-        for (int k = threadIdx.x; k < ns; k += blockDim.x) samp[r][k] = keys[static_cast<size_t>(r) * a.R + (static_cast<size_t>(k) << sh)];
-    }
-    __syncthreads();
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += gridDim.x * blockDim.x) {
-        if (t == n) {   // sentinel of the exclusive scans over n + 1 entries
-            a.w3[n] = 0.0; a.w3[a.stride + n] = 0.0; a.w3[2 * a.stride + n] = 0.0;
-            continue;
+        if (blockIdx.x == 0) {
+            a.st->n_part = o;
+            a.w3[o] = 0.0; a.w3[a.stride + o] = 0.0; a.w3[2 * a.stride + o] = 0.0;   // sentinel of the scans over n + 1 entries
         }
-        int s = 0;
-        while (s + 1 < a.nparts && t >= off[s + 1]) s++;
-        const int i = t - off[s];
-        const unsigned long long k = keys[static_cast<size_t>(s) * a.R + i];
-        int pos = i;
-        for (int r = 0; r < a.nparts; r++) {
-            if (r == s || cnt[r] == 0) continue;
-            // rank of k in run r: elements < k, or <= k for runs of lower source rank (ties: lower source first).
-            // Coarse step on the cached samples, fine step inside one S-wide window of the run.
-            const bool le = r < s;
-            const int ns = (cnt[r] + S - 1) >> sh;
-            int l = 0, h = ns;
-            while (l < h) { const int mid = (l + h) >> 1; const unsigned long long v = samp[r][mid]; if (le ? v <= k : v < k) l = mid + 1; else h = mid; }
-            if (l > 0) {
-                const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
-                int lo2 = ((l - 1) << sh) + 1, hi2 = min(l << sh, cnt[r]);
-                while (lo2 < hi2) { const int mid = (lo2 + hi2) >> 1; const unsigned long long v = kr[mid]; if (le ? v <= k : v < k) lo2 = mid + 1; else hi2 = mid; }
-                pos += lo2;
+    }
+    __syncthreads();
+    const int n = off[a.nparts];
+    const int ntiles = (n + 255) >> 8;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int t0 = tile << 8, t1 = min(t0 + 255, n - 1);
+        if (threadIdx.x < a.nparts) {   // key range of the tile: runs are sorted, so the ends of every run segment inside it
+            const int r = threadIdx.x;
+            const int lo = max(t0, off[r]), hi = min(t1, off[r + 1] - 1);
+            rmin[r] = ~0ull; rmax[r] = 0ull;
+            if (lo <= hi) {
+                rmin[r] = keys[static_cast<size_t>(r) * a.R + (lo - off[r])];
+                rmax[r] = keys[static_cast<size_t>(r) * a.R + (hi - off[r])];
             }
         }
-        const float4 rc = recs[static_cast<size_t>(s) * a.R + i];
-        a.mkeys[pos] = k;
-        a.sx[pos] = rc.x; a.sy[pos] = rc.y; a.sm[pos] = rc.z; a.gidx[pos] = __float_as_int(rc.w);
-        a.w3[pos] = rc.z;
-        a.w3[a.stride + pos] = static_cast<double>(rc.z) * rc.x;
-        a.w3[2 * a.stride + pos] = static_cast<double>(rc.z) * rc.y;
+        __syncthreads();
+        if (threadIdx.x < a.nparts) {
+            unsigned long long kmin = ~0ull, kmax = 0ull;
+            for (int r = 0; r < a.nparts; r++) { kmin = min(kmin, rmin[r]); kmax = max(kmax, rmax[r]); }
+            const int r = threadIdx.x;
+            const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
+            int l = 0, h = cnt[r];
+            while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] < kmin) l = mid + 1; else h = mid; }
+            wlo[r] = l;
+            h = cnt[r];   // the upper end is at or after the lower one
+            while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] <= kmax) l = mid + 1; else h = mid; }
+            whi[r] = l;
+        }
+        __syncthreads();
+        const int t = t0 + threadIdx.x;
+        if (t < n) {
+            int s = 0;
+            while (s + 1 < a.nparts && t >= off[s + 1]) s++;
+            const int i = t - off[s];
+            const unsigned long long k = keys[static_cast<size_t>(s) * a.R + i];
+            int pos = i;
+            for (int r = 0; r < a.nparts; r++) {
+                if (r == s || cnt[r] == 0) continue;
+                // rank of k in run r: elements < k, or <= k for runs of lower source rank (ties: lower source first)
+                const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
+                int l = wlo[r], h = whi[r];
+                if (r < s) { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] <= k) l = mid + 1; else h = mid; } }
+                else       { while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] < k) l = mid + 1; else h = mid; } }
+                pos += l;
+            }
+            const float4 rc = recs[static_cast<size_t>(s) * a.R + i];
+            a.mkeys[pos] = k;
+            a.sx[pos] = rc.x; a.sy[pos] = rc.y; a.sm[pos] = rc.z; a.gidx[pos] = __float_as_int(rc.w);
+            a.w3[pos] = rc.z;
+            a.w3[a.stride + pos] = static_cast<double>(rc.z) * rc.x;
+            a.w3[2 * a.stride + pos] = static_cast<double>(rc.z) * rc.y;
+        }
+        __syncthreads();
     }
 }
 
@@ -2118,7 +2133,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             PartBufs& P = w.parts[r];
             const size_t stride = P.cap + 1;
             MergeArgs ma{P.arena, lay.off_in_key, lay.off_in_rec, lay.off_count_in, lay.R, nparts, P.mkeys, P.sx, P.sy, P.sm, P.gidx, P.w3, stride, P.status};
-            bhp_merge_kernel<<<std::min(GE, e.num_sms * 2), T, 0, s>>>(ma);
+            bhp_merge_kernel<<<GE, T, 0, s>>>(ma);
             launch_scan<double>(s, P.w3, P.p3, P.tile_sums, 3, static_cast<int>(P.cap) + 1, &P.status->n_part, 1, stride, e.num_sms * 4);
             e.ctr.kernel_launches += 4;
         }
