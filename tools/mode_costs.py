@@ -11,6 +11,7 @@ from rust_exp_b200 import binding, ic  # noqa: E402
 
 lib = pkg.load()
 lib.init(0)
+lib.set_async(True)   # back-to-back steps: device time per step (the default synchronous calls add a host round trip each)
 
 
 def timeit(fn, reps):
