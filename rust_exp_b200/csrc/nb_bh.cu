@@ -981,12 +981,14 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
             my_pops++;
             if (o0 | o1 | o2 | o3) {
                 const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
-                // push order 3..0 so that child 0 is opened first (DFS-like order).  Branch-free: every lane stores the
-                // same (warp-uniform) entry to the same slot, and the slot only counts if its lane mask is non-empty.
-                s[sp] = make_uint2(C.w, o3); sp += (o3 != 0u);
-                s[sp] = make_uint2(C.z, o2); sp += (o2 != 0u);
-                s[sp] = make_uint2(C.y, o1); sp += (o1 != 0u);
-                s[sp] = make_uint2(C.x, o0); sp += (o0 != 0u);
+                // stack order bottom -> top: child 3, 2, 1, 0 (non-empty masks only), so that child 0 is opened first (DFS-like
+                // order).  Lane j < 4 stores child 3-j at its final slot: one writer per slot, no ordering between stores needed.
+                const int nz3 = o3 != 0u, nz2 = o2 != 0u, nz1 = o1 != 0u, nz0 = o0 != 0u;
+                const unsigned my_o = lane == 0 ? o3 : (lane == 1 ? o2 : (lane == 2 ? o1 : o0));
+                const int my_c = lane == 0 ? C.w : (lane == 1 ? C.z : (lane == 2 ? C.y : C.x));
+                const int my_pos = sp + (lane > 0 ? nz3 : 0) + (lane > 1 ? nz2 : 0) + (lane > 2 ? nz1 : 0);
+                if (lane < 4 && my_o != 0u) s[my_pos] = make_uint2(static_cast<unsigned>(my_c), my_o);
+                sp += nz3 + nz2 + nz1 + nz0;
             }
             __syncwarp();
         }
@@ -1225,6 +1227,7 @@ static int traverse_resident_blocks(Engine& e) {
     if (!per_sm) {
         NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, false>, kTravWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
+        if (const char* v = getenv("NB_BH_WALK_BLOCKS")) { const int c = atoi(v); if (c >= 1 && c < per_sm) per_sm = c; }   // experiments
     }
     return per_sm * e.num_sms;
 }
@@ -2370,6 +2373,10 @@ void bh_step(Engine& e, float theta, float dt) {
             NB_CUDA(cudaStreamEndCapture(e.stream, &graph));
             w.capturing = false;
             bool updated = false;
+            // a different n / sort depth / part count / box option changes the number or shape of the launches: no point in
+            // asking for an in-place update then (it would be refused); theta, dt and reallocations only change parameters
+            const bool same_topology = g.exec && g.n == e.n && g.sort_levels == w.sort_levels && g.nparts == nparts_now && g.square == e.square_aabb;
+            if (g.exec && !same_topology) { NB_CUDA(cudaGraphExecDestroy(g.exec)); g.exec = nullptr; }
             if (g.exec) {
                 cudaGraphExecUpdateResultInfo info;
                 if (cudaGraphExecUpdate(g.exec, graph, &info) == cudaSuccess) updated = true;
