@@ -982,13 +982,12 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
             if (o0 | o1 | o2 | o3) {
                 const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
                 // stack order bottom -> top: child 3, 2, 1, 0 (non-empty masks only), so that child 0 is opened first (DFS-like
-                // order).  Lane j < 4 stores child 3-j at its final slot: one writer per slot, no ordering between stores needed.
-                const int nz3 = o3 != 0u, nz2 = o2 != 0u, nz1 = o1 != 0u, nz0 = o0 != 0u;
-                const unsigned my_o = lane == 0 ? o3 : (lane == 1 ? o2 : (lane == 2 ? o1 : o0));
-                const int my_c = lane == 0 ? C.w : (lane == 1 ? C.z : (lane == 2 ? C.y : C.x));
-                const int my_pos = sp + (lane > 0 ? nz3 : 0) + (lane > 1 ? nz2 : 0) + (lane > 2 ? nz1 : 0);
-                if (lane < 4 && my_o != 0u) s[my_pos] = make_uint2(static_cast<unsigned>(my_c), my_o);
-                sp += nz3 + nz2 + nz1 + nz0;
+                // order).  The masks are warp-uniform: every lane stores the same entry to the same slot, and a slot is only
+                // ever written when it is kept (no two different values meet in one slot between two warp syncs).
+                if (o3 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.w), o3); sp++; }
+                if (o2 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.z), o2); sp++; }
+                if (o1 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.y), o1); sp++; }
+                if (o0 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.x), o0); sp++; }
             }
             __syncwarp();
         }
