@@ -589,10 +589,13 @@ struct BuildArgs {
     unsigned part_off;   // added to every child block index (global block index space of partitioned trees)
     int cut_level;       // partitioned build: interior nodes at levels >= cut_level are counted in n_deep
     struct NodeInfo* info;   // EXACT parallel build: per interior node its body range, level and own record slot
-    int store_sq;            // FAST: the 4th record field is s*s (the walk's opening test compares squares); EXACT: s
+    float q_scale;           // FAST: 1/theta^2 -- the 4th record field is qrec(s, q_scale), the folded opening test; EXACT (0): s
     const int* n_dev;        // partitioned step: the number of bodies only exists on the device (overrides n)
     size_t stride;           // plane stride of p3 (n + 1 for the single tree, capacity + 1 for a part)
 };
+// The FAST walk's opening test, folded into the record by the build: s/d < theta (rs-src/nbody.rs:345)  <=>
+// s^2/theta^2 + EPS < d^2 + EPS.  theta so small that 1/theta^2 overflows gives +inf (or NaN for s = 0): never accepted.
+__device__ __forceinline__ float qrec(float s, float inv_theta2) { return __fmaf_rn(__fmul_rn(s, s), inv_theta2, kEps); }
 __device__ __forceinline__ int build_n(const BuildArgs& a) { return a.n_dev ? *a.n_dev : a.n; }
 
 __device__ __forceinline__ int interior_id(const BuildArgs& a, int first, int level) {
@@ -685,7 +688,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
             a.nblk[1] = make_float4(static_cast<float>((a.p3[2 * stride + n] - a.p3[2 * stride]) / M), 0.f, 0.f, 0.f);
             a.nblk[2] = make_float4(static_cast<float>(M), 0.f, 0.f, 0.f);
             const float s0 = __fsub_rn(x2, x1);
-            a.nblk[3] = make_float4(a.store_sq ? __fmul_rn(s0, s0) : s0, -1.f, -1.f, -1.f);
+            a.nblk[3] = make_float4(a.q_scale != 0.f ? qrec(s0, a.q_scale) : s0, -1.f, -1.f, -1.f);
             a.ncblk[0] = make_int4(static_cast<int>(a.part_off) + blk, -1, -1, -1);
         }
         float4 rec[4];
@@ -710,7 +713,7 @@ __global__ void bh_emit_kernel(const BuildArgs a, const int* __restrict__ owner,
                     // child cell width s = x2 - x1 (rs-src/nbody.rs:341), children per :295-300
                     const float s = (q & 1) ? __fsub_rn(x2, cx) : __fsub_rn(cx, x1);
                     rec[q] = make_float4(static_cast<float>(MX / M), static_cast<float>(MY / M), static_cast<float>(M),
-                                         a.store_sq ? __fmul_rn(s, s) : s);
+                                         a.q_scale != 0.f ? qrec(s, a.q_scale) : s);
                     chp[q] = static_cast<int>(a.part_off) + 1 + cid;
                     if (a.info) { a.info[cid].blk = blk; a.info[cid].slot_level = q | ((l + 1) << 8); }
                 } else {
@@ -800,21 +803,47 @@ __global__ void bh_finalize_exact_kernel(int cap_nodes, float4* ndata, const flo
 // ---- traversal, FAST ---------------------------------------------------------------------------------------
 // One warp per 32 Morton-consecutive bodies; warps fetch groups from a ticket counter (persistent grid, no tail).
 // Stack entries are (node block, mask of lanes that must look at it).  A block is the four children of an opened
-// node in SoA form (x[4] y[4] m[4] q[4], 64 bytes; q = s*s of the child's cell for an interior child, -1 for a
-// leaf or an empty slot): the warp evaluates all four branch-free with packed FP32.  A lane in the mask interacts
-// with a child if it passes the reference's per-body opening test s/d < theta (rs-src/nbody.rs:345, as
-// s^2 < theta^2 d^2) -- which a leaf's q = -1 always passes -- otherwise it asks for the child to be opened; only
-// children that some lane must open are pushed, with that lane mask.  Every body therefore evaluates exactly the
-// reference's interaction list (:333-377).  Empty leaves (m = 0, :367) and the body's own leaf (d = 0, :365) need
-// no test: their contribution is an exact zero because EPS > 0.
-// Lanes outside an entry's mask run with theta^2 = NaN: both `q < t` and the derived open mask are then false
-// without any per-child predicate logic.
-constexpr int kSparseLanes = 8;   // entries that concern at most this many bodies are batched four at a time
-template <bool COUNT, bool PARTS, bool SPARSE>
-__global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_fast_kernel(
+// node in SoA form (x[4] y[4] m[4] q[4], 64 bytes): the warp evaluates all four branch-free with packed FP32.
+// q is the opening test folded into one number by the build (qrec()): for an interior child q = s^2/theta^2 + EPS, so
+// that the reference's per-body test s/d < theta (rs-src/nbody.rs:345) reads q < d^2 + EPS -- the right-hand side is
+// the denominator of the force law, which the lane computes anyway; a leaf or an empty slot has q = -1 and always
+// passes.  A lane of the mask that fails the test asks for the child to be opened; only children that some lane must
+// open are pushed, with that lane mask.  Every body therefore evaluates exactly the reference's interaction list
+// (:333-377).  Empty leaves (m = 0, :367) and the body's own leaf (d = 0, :365) need no test: their contribution is
+// an exact zero because EPS > 0.
+// The lane's membership of the entry's mask is the third input of the comparison (one FSETP yields both "accepts"
+// and "must open"), so lanes outside the mask cost no extra instruction and never contribute.
+__device__ __forceinline__ uint2 stack_load(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+// push (block, mask) if the mask is not empty.  The mask is warp-uniform: every lane stores the same entry to the same
+// slot, and a slot only ever receives one value between two warp syncs.
+__device__ __forceinline__ void stack_push_if(unsigned& addr, unsigned block, unsigned mask) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.v2.u32 [%0], {%1, %2};\n\t@p add.u32 %0, %0, 8;\n\t}"
+        : "+r"(addr) : "r"(block), "r"(mask) : "memory");
+}
+// One child of the popped block for one lane: c = the lane's (m * 1/(d^2+EPS)) for that child, kept only if the lane is in the
+// entry's mask and passes the opening test q < d^2+EPS; returns the ballot of the mask's lanes that fail it (must open).
+// One dual-output FSETP gives both predicates, with the mask membership as its third input.
+__device__ __forceinline__ unsigned test_child(float q, float e, unsigned in_mask, float& c) {
+    unsigned open;
+    asm volatile(
+        "{\n\t.reg .pred pa, pr, pm;\n\t"
+        "setp.ne.u32 pm, %4, 0;\n\t"
+        "setp.lt.and.f32 pa|pr, %2, %3, pm;\n\t"
+        "selp.f32 %0, %0, 0f00000000, pa;\n\t"
+        "vote.sync.ballot.b32 %1, pr, 0xffffffff;\n\t}"
+        : "+f"(c), "=r"(open) : "f"(q), "f"(e), "r"(in_mask));
+    return open;
+}
+template <bool COUNT, bool PARTS, int MINB>
+__global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
-    float theta2, BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
+    BhStatus* st, int ticket_slot, const unsigned long long* __restrict__ keys_sorted,
     unsigned* __restrict__ cell_work, const int* __restrict__ n_dev, const uint32_t* __restrict__ epoch_dev) {
     __shared__ uint2 stk[kTravWarps][kStackPerWarp];
     if (cell_work != nullptr && epoch_dev != nullptr) cell_work += (*epoch_dev & 1u) * kNumCells;   // this step's parity
@@ -822,9 +851,8 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
     const unsigned lanebit = 1u << lane;
     if (n_dev) n_list = *n_dev;     // partitioned step: the size of the part's body list only exists on the device
     const int ngroups = (n_list + 31) >> 5;
-    const float qnan = __int_as_float(0x7fffffff);
     const float2 eps2 = make_float2(kEps, kEps);
-    uint2* s = stk[warp];
+    const unsigned sbase = static_cast<unsigned>(__cvta_generic_to_shared(stk[warp]));
     unsigned long long n_int = 0, n_vis = 0, n_pop = 0, n_lane = 0;
     for (;;) {
         int w = 0;
@@ -837,115 +865,19 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
         const float px = sx[pos], py = sy[pos];
         const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
         float2 ax = make_float2(0.f, 0.f), ay = make_float2(0.f, 0.f);
-        int sp = 1;
+        unsigned sa = sbase;          // shared-memory address of the first free stack slot
         unsigned my_pops = 0;
         {
             const unsigned m0 = __ballot_sync(0xffffffffu, live);
-            if (lane == 0) s[0] = make_uint2(tt.root, m0);   // root block = {root, empty, empty, empty}
+            stack_push_if(sa, tt.root, m0);             // root block = {root, empty, empty, empty}
             __syncwarp();
             if (COUNT) n_vis -= live ? 3 : 0;           // the three padding slots of block 0 are not nodes
         }
-        while (sp > 0) {
-            const uint2 e = s[sp - 1];
-            if (SPARSE && __popc(e.y) <= kSparseLanes) {
-                // ---- sparse pass: up to four entries that each concern <= 8 bodies are evaluated together, one entry per
-                // octet of lanes, lane j of an octet standing in for the j-th body of its entry (siblings pushed by one
-                // pop sit next to each other on the stack, so the batch usually fills).  Same arithmetic per (body, child).
-                uint2 E1 = make_uint2(0u, 0u), E2 = E1, E3 = E1;
-                int k = 1;
-                if (sp >= 2) {
-                    E1 = s[sp - 2];
-                    if (__popc(E1.y) <= kSparseLanes) {
-                        k = 2;
-                        if (sp >= 3) {
-                            E2 = s[sp - 3];
-                            if (__popc(E2.y) <= kSparseLanes) {
-                                k = 3;
-                                if (sp >= 4) { E3 = s[sp - 4]; if (__popc(E3.y) <= kSparseLanes) k = 4; }
-                            }
-                        }
-                    }
-                }
-                if (k < 2) E1.y = 0u;
-                if (k < 3) E2.y = 0u;
-                if (k < 4) E3.y = 0u;
-                sp -= k;
-                __syncwarp();
-                const int oct = lane >> 3, j = lane & 7;
-                const uint2 eo = oct == 0 ? e : (oct == 1 ? E1 : (oct == 2 ? E2 : E3));
-                const unsigned b = __fns(eo.y, 0u, j + 1);          // lane that owns the j-th body of this octet's entry
-                const bool act = b < 32u;
-                const float qx = __shfl_sync(0xffffffffu, px, act ? b : lane), qy = __shfl_sync(0xffffffffu, py, act ? b : lane);
-                const float thx = act ? theta2 : qnan;
-                unsigned part = 0, bi = eo.x;
-                const float4* __restrict__ nb4;
-                if (PARTS) {
-                    part = eo.x >> kPartShift; bi = eo.x & ((1u << kPartShift) - 1u);
-                    nb4 = tt.blk[part] + 4 * static_cast<size_t>(bi);
-                } else {
-                    nb4 = tt.blk[0] + 4 * static_cast<size_t>(bi);
-                }
-                const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), Q = __ldg(nb4 + 3);
-                const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy);
-                const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), nqx), dx23 = __fadd2_rn(make_float2(X.z, X.w), nqx);
-                const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), nqy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), nqy);
-                const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
-                const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
-                const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
-                const float2 t01 = __fmul2_rn(d01, make_float2(thx, thx)), t23 = __fmul2_rn(d23, make_float2(thx, thx));
-                const bool a0 = Q.x < t01.x, a1 = Q.y < t01.y, a2 = Q.z < t23.x, a3 = Q.w < t23.y;
-                float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
-                float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
-                c01.x = a0 ? c01.x : 0.f; c01.y = a1 ? c01.y : 0.f;
-                c23.x = a2 ? c23.x : 0.f; c23.y = a3 ? c23.y : 0.f;
-                const float2 tx = __ffma2_rn(c23, dx23, __fmul2_rn(c01, dx01)), ty = __ffma2_rn(c23, dy23, __fmul2_rn(c01, dy01));
-                const float cax = tx.x + tx.y, cay = ty.x + ty.y;
-                // hand every (entry, body) contribution back to the lane that owns the body
-#pragma unroll
-                for (int o = 0; o < 4; o++) {
-                    const unsigned mo = o == 0 ? e.y : (o == 1 ? E1.y : (o == 2 ? E2.y : E3.y));
-                    if (o < k) {
-                        const int srcl = 8 * o + __popc(mo & (lanebit - 1u));
-                        const float vx = __shfl_sync(0xffffffffu, cax, srcl), vy = __shfl_sync(0xffffffffu, cay, srcl);
-                        if (mo & lanebit) { ax.x += vx; ay.x += vy; }
-                    }
-                }
-                // bodies that did not accept child c must open it: one new lane mask per (entry, child), reduced inside the octet
-                const unsigned bit = act ? (1u << b) : 0u;
-                const unsigned omask = 0xffu << (8 * oct);
-                const unsigned n0 = __reduce_or_sync(omask, a0 ? 0u : bit), n1 = __reduce_or_sync(omask, a1 ? 0u : bit);
-                const unsigned n2 = __reduce_or_sync(omask, a2 ? 0u : bit), n3 = __reduce_or_sync(omask, a3 ? 0u : bit);
-                const int cnt = (n0 != 0u) + (n1 != 0u) + (n2 != 0u) + (n3 != 0u);
-                const int c0 = __shfl_sync(0xffffffffu, cnt, 0), c1 = __shfl_sync(0xffffffffu, cnt, 8);
-                const int c2 = __shfl_sync(0xffffffffu, cnt, 16), c3 = __shfl_sync(0xffffffffu, cnt, 24);
-                if (COUNT) {
-                    n_vis += act ? 4 : 0;
-                    n_int += (a0 && M.x != 0.f && !(X.x == qx && Y.x == qy)) + (a1 && M.y != 0.f && !(X.y == qx && Y.y == qy)) +
-                             (a2 && M.z != 0.f && !(X.z == qx && Y.z == qy)) + (a3 && M.w != 0.f && !(X.w == qx && Y.w == qy));
-                    const int lanes = __popc(e.y) + __popc(E1.y) + __popc(E2.y) + __popc(E3.y);
-                    if (lane == 0) { n_pop++; n_lane += lanes; atomicAdd(&st->pop_hist[lanes], 1ull); }
-                }
-                my_pops++;
-                if (c0 + c1 + c2 + c3) {
-                    // reverse octet order: octet 0 held the former top of the stack, its children end up on top again;
-                    // inside an octet child 3 lowest, child 0 on top.  Lanes 0..3 of an octet store one child each.
-                    const int base = sp + (oct < 3 ? c3 : 0) + (oct < 2 ? c2 : 0) + (oct < 1 ? c1 : 0);
-                    if (cnt != 0 && j < 4) {
-                        const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
-                        const unsigned nm = j == 0 ? n0 : (j == 1 ? n1 : (j == 2 ? n2 : n3));
-                        const unsigned cb = static_cast<unsigned>(j == 0 ? C.x : (j == 1 ? C.y : (j == 2 ? C.z : C.w)));
-                        const int above = ((j < 3) && n3 != 0u) + ((j < 2) && n2 != 0u) + ((j < 1) && n1 != 0u);
-                        if (nm != 0u) s[base + above] = make_uint2(cb, nm);
-                    }
-                    sp += c0 + c1 + c2 + c3;
-                }
-                __syncwarp();
-                continue;
-            }
-            --sp;
+        while (sa != sbase) {
+            sa -= 8u;
+            const uint2 e = stack_load(sa);
             __syncwarp();
-            const bool act = (e.y & lanebit) != 0u;
-            const float thx = act ? theta2 : qnan;
+            const unsigned in_mask = e.y & lanebit;
             const float4* __restrict__ nb4;
             unsigned part = 0, bi = e.x;
             if (PARTS) {
@@ -957,37 +889,31 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
             const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), Q = __ldg(nb4 + 3);
             const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
             const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
-            const float2 d01 = __ffma2_rn(dy01, dy01, __fmul2_rn(dx01, dx01));
-            const float2 d23 = __ffma2_rn(dy23, dy23, __fmul2_rn(dx23, dx23));
-            const float2 e01 = __fadd2_rn(d01, eps2), e23 = __fadd2_rn(d23, eps2);
-            // opening test s/d < theta  <=>  s^2 < theta^2 d^2 ; false for every child when the lane is not in the mask
-            const float2 t01 = __fmul2_rn(d01, make_float2(thx, thx)), t23 = __fmul2_rn(d23, make_float2(thx, thx));
-            const bool a0 = Q.x < t01.x, a1 = Q.y < t01.y, a2 = Q.z < t23.x, a3 = Q.w < t23.y;
+            // d^2 + EPS: the denominator of the force law (rs-src/nbody.rs:180) and the right-hand side of the opening test
+            const float2 e01 = __ffma2_rn(dy01, dy01, __ffma2_rn(dx01, dx01, eps2));
+            const float2 e23 = __ffma2_rn(dy23, dy23, __ffma2_rn(dx23, dx23, eps2));
             float2 c01 = __fmul2_rn(make_float2(M.x, M.y), make_float2(rcp_approx(e01.x), rcp_approx(e01.y)));
             float2 c23 = __fmul2_rn(make_float2(M.z, M.w), make_float2(rcp_approx(e23.x), rcp_approx(e23.y)));
-            c01.x = a0 ? c01.x : 0.f; c01.y = a1 ? c01.y : 0.f;
-            c23.x = a2 ? c23.x : 0.f; c23.y = a3 ? c23.y : 0.f;
+            const unsigned o0 = test_child(Q.x, e01.x, in_mask, c01.x), o1 = test_child(Q.y, e01.y, in_mask, c01.y);
+            const unsigned o2 = test_child(Q.z, e23.x, in_mask, c23.x), o3 = test_child(Q.w, e23.y, in_mask, c23.y);
             ax = __ffma2_rn(c01, dx01, ax); ay = __ffma2_rn(c01, dy01, ay);
             ax = __ffma2_rn(c23, dx23, ax); ay = __ffma2_rn(c23, dy23, ay);
-            // lanes of the mask that did not accept child k must open it
-            const unsigned o0 = e.y & ~__ballot_sync(0xffffffffu, a0), o1 = e.y & ~__ballot_sync(0xffffffffu, a1);
-            const unsigned o2 = e.y & ~__ballot_sync(0xffffffffu, a2), o3 = e.y & ~__ballot_sync(0xffffffffu, a3);
             if (COUNT) {
+                const bool act = in_mask != 0u;
+                const bool a0 = act && Q.x < e01.x, a1 = act && Q.y < e01.y, a2 = act && Q.z < e23.x, a3 = act && Q.w < e23.y;
                 n_vis += act ? 4 : 0;
                 n_int += (a0 && M.x != 0.f && !(X.x == px && Y.x == py)) + (a1 && M.y != 0.f && !(X.y == px && Y.y == py)) +
                          (a2 && M.z != 0.f && !(X.z == px && Y.z == py)) + (a3 && M.w != 0.f && !(X.w == px && Y.w == py));
                 if (lane == 0) { n_pop++; n_lane += __popc(e.y); atomicAdd(&st->pop_hist[__popc(e.y)], 1ull); }
             }
-            my_pops++;
+            if (PARTS) my_pops++;
             if (o0 | o1 | o2 | o3) {
                 const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
-                // stack order bottom -> top: child 3, 2, 1, 0 (non-empty masks only), so that child 0 is opened first (DFS-like
-                // order).  The masks are warp-uniform: every lane stores the same entry to the same slot, and a slot is only
-                // ever written when it is kept (no two different values meet in one slot between two warp syncs).
-                if (o3 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.w), o3); sp++; }
-                if (o2 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.z), o2); sp++; }
-                if (o1 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.y), o1); sp++; }
-                if (o0 != 0u) { s[sp] = make_uint2(static_cast<unsigned>(C.x), o0); sp++; }
+                // stack order bottom -> top: child 3, 2, 1, 0 (non-empty masks only), so that child 0 is opened first
+                stack_push_if(sa, static_cast<unsigned>(C.w), o3);
+                stack_push_if(sa, static_cast<unsigned>(C.z), o2);
+                stack_push_if(sa, static_cast<unsigned>(C.y), o1);
+                stack_push_if(sa, static_cast<unsigned>(C.x), o0);
             }
             __syncwarp();
         }
@@ -996,7 +922,7 @@ __global__ void __launch_bounds__(kTravWarps * 32, SPARSE ? 5 : 6) bh_traverse_f
             const int own = gi / tt.shard_len;
             tt.acc[own][gi - own * tt.shard_len] = make_float2(ax.x + ax.y, ay.x + ay.y);
         }
-        if (cell_work != nullptr && lane == 0)   // partition weights for the next step: walk cost per cut-level cell
+        if (PARTS && cell_work != nullptr && lane == 0)   // partition weights for the next step: walk cost per cut-level cell
             atomicAdd(&cell_work[static_cast<unsigned>(keys_sorted[pos] >> kCellShift)], my_pops);
     }
     if (COUNT) {
@@ -1221,10 +1147,19 @@ static int bh_partition_count(const Engine& e) {
     return parts > 1 ? parts : 1;
 }
 
+// Resident CTAs per SM the walk is compiled for (its register budget follows: 6 -> 40 registers, 7 -> 36): NB_BH_WALK_MINB
+// selects the 5 / 6 / 7 variant for experiments; NB_BH_WALK_BLOCKS only shrinks the persistent grid.
+static int walk_minb() {
+    static const int v = [] { const char* s = getenv("NB_BH_WALK_MINB"); const int c = s ? atoi(s) : 6; return (c == 5 || c == 7) ? c : 6; }();
+    return v;
+}
 static int traverse_resident_blocks(Engine& e) {
     static int per_sm = 0;
     if (!per_sm) {
-        NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, false>, kTravWarps * 32, 0));
+        const int mb = walk_minb();
+        if (mb == 5) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 5>, kTravWarps * 32, 0));
+        else if (mb == 7) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 7>, kTravWarps * 32, 0));
+        else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 6>, kTravWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
         if (const char* v = getenv("NB_BH_WALK_BLOCKS")) { const int c = atoi(v); if (c >= 1 && c < per_sm) per_sm = c; }   // experiments
     }
@@ -1233,19 +1168,16 @@ static int traverse_resident_blocks(Engine& e) {
 
 // ticket_slot: which st->tickets[] counter this launch draws its groups from (one per launch between two resets)
 static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, const float* sy, const int* idx_sorted,
-                            const int* mine, int n_list, float theta, BhStatus* st, int ticket_slot = 0,
+                            const int* mine, int n_list, BhStatus* st, int ticket_slot = 0,
                             const unsigned long long* keys_sorted = nullptr, unsigned* cell_work = nullptr, const int* n_dev = nullptr,
                             const uint32_t* epoch_dev = nullptr) {
     // n_dev given: n_list is only an estimate for sizing the (persistent) grid
     const int want = std::max(1, (n_list + kTravWarps * 32 - 1) / (kTravWarps * 32));
     const int blocks = std::min(want, traverse_resident_blocks(e));
     const bool parts = tt.shift != 31;
-    const float th2 = theta * theta;
-    // The sparse (octet) pass is an experiment that LOST (profiles/r02_walk_sparse_pass_ab.jsonl: 1.7x slower -- the
-    // sub-warp collectives it needs compile to WARPSYNC/ENDCOLLECTIVE loops): off unless NB_BH_SPARSE=1.
-    static const bool sparse = [] { const char* v = getenv("NB_BH_SPARSE"); return v ? atoi(v) != 0 : false; }();
-#define NB_TRAV(C, P, S) bh_traverse_fast_kernel<C, P, S><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, th2, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
-#define NB_TRAV2(C, P) do { if (sparse) NB_TRAV(C, P, true); else NB_TRAV(C, P, false); } while (0)
+    const int mb = walk_minb();
+#define NB_TRAV(C, P, B) bh_traverse_fast_kernel<C, P, B><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
+#define NB_TRAV2(C, P) do { if (mb == 5) NB_TRAV(C, P, 5); else if (mb == 7) NB_TRAV(C, P, 7); else NB_TRAV(C, P, 6); } while (0)
     if (e.bh_count) { if (parts) NB_TRAV2(true, true); else NB_TRAV2(true, false); }
     else { if (parts) NB_TRAV2(false, true); else NB_TRAV2(false, false); }
 #undef NB_TRAV2
@@ -1315,7 +1247,8 @@ static GlobalPos global_positions(Engine& e) {
 }
 
 // keys -> sort -> gather/scan -> single-pass build of ONE tree over all n bodies (nblk / ncblk)
-static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, NodeInfo* info) {
+static float inv_theta2(float theta) { return 1.0f / (theta * theta); }
+static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, NodeInfo* info, float theta) {
     cudaStream_t s = e.stream;
     const int T = 256, G = (n + T - 1) / T;
     // EXACT (info != nullptr) keeps the full sort: its per-level index sorts below rely on w.idx staying the identity
@@ -1346,7 +1279,7 @@ static void build_single_tree(Engine& e, BhWork& w, const GlobalPos& gp, int n, 
         size_t tb = w.cub_bytes;
         cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.base, n, s);   // integer: deterministic
         BuildArgs ba{w.keys_sorted, w.sx, w.sy, w.sm, w.p3, w.dcap, w.base, w.nblk, w.ncblk, n, (w.cap_nodes - 4) / 4, 0u, 0, info,
-                     info ? 0 : 1, nullptr, stride};
+                     info ? 0.f : inv_theta2(theta), nullptr, stride};
         bh_owner_kernel<<<G, T, 0, s>>>(ba, w.owner, w.status);
         bh_emit_kernel<<<std::min(G, e.num_sms * 8), T, 0, s>>>(ba, w.owner, w.status);
         e.ctr.kernel_launches += 4;
@@ -1400,7 +1333,7 @@ static void bh_forces(Engine& e, float theta) {
             cub::DeviceRadixSort::SortPairs(w.cub_tmp, tb, w.xk, w.xk_sorted, w.idx, w.xorder, n, 0, 32, s);
             bh_close_scan_kernel<<<G, T, 0, s>>>(w.xorder, gp.x, gp.y, n, w.xflags);
             // (b) the refinement tree, with per-node body ranges
-            build_single_tree(e, w, gp, n, w.info);
+            build_single_tree(e, w, gp, n, w.info, theta);
             bh_maxdelta_kernel<<<G, T, 0, s>>>(w.delta, w.dcap, n, w.xflags);
             e.ctr.kernel_launches += 3;
             NB_CUDA(cudaMemcpyAsync(w.xflags_host, w.xflags, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1448,7 +1381,7 @@ static void bh_forces(Engine& e, float theta) {
             w.last_nparts = 0;
         }
     } else {
-        build_single_tree(e, w, gp, n, nullptr);
+        build_single_tree(e, w, gp, n, nullptr, theta);
         const int* mine = nullptr;
         int n_list = n;
         if (e.dist && e.world > 1) {
@@ -1466,7 +1399,7 @@ static void bh_forces(Engine& e, float theta) {
             tt.acc[e.rank] = w.acc;
             tt.shift = 31; tt.root = 0u; tt.shard_len = static_cast<int>(e.lay.L);
             w.last_tt = tt; w.last_nparts = 1;
-            launch_traverse(e, tt, w.sx, w.sy, w.order, mine, n_list, theta, w.status);
+            launch_traverse(e, tt, w.sx, w.sy, w.order, mine, n_list, w.status);
         }
     }
     NB_CUDA(cudaGetLastError());
@@ -1771,6 +1704,7 @@ struct TopArgs {
     int* tcount; double* tm3; float4* tleaf; int* tchild;
     float4* blk; int4* cblk;
     unsigned top_off;                  // part id of the top tree << kPartShift
+    float q_scale;                     // 1/theta^2 (see qrec())
 };
 
 __device__ __forceinline__ int top_off_level(int l) { return ((1 << (2 * l)) - 1) / 3; }
@@ -1868,7 +1802,7 @@ __global__ void __launch_bounds__(256) bh_top_build_kernel(const TopArgs a, BhSt
         const double M = a.tm3[node];
         const float cw = cell_width(st, level, path);
         rec = make_float4(static_cast<float>(a.tm3[kTopNodes + node] / M), static_cast<float>(a.tm3[2 * kTopNodes + node] / M),
-                          static_cast<float>(M), __fmul_rn(cw, cw));
+                          static_cast<float>(M), qrec(cw, a.q_scale));
         child = ch;
     };
     // block 0: {root, empty, empty, empty}; block 1 + node: the four children of interior top node `node`
@@ -2151,7 +2085,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             launch_scan<int>(s, P.count, P.base, P.itile, 1, static_cast<int>(P.cap), nd, 0, 0, e.num_sms * 4);
             BuildArgs ba{P.mkeys, P.sx, P.sy, P.sm, P.p3, P.dcap, P.base, reinterpret_cast<float4*>(P.arena + lay.off_nblk),
                          reinterpret_cast<int4*>(P.arena + lay.off_ncblk), 0, P.cap_blocks - 2,
-                         static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, 1, nd, P.cap + 1};
+                         static_cast<unsigned>(part_id(r)) << kPartShift, kCutLevel, nullptr, inv_theta2(theta), nd, P.cap + 1};
             bh_owner_kernel<<<GE, T, 0, s>>>(ba, P.owner, P.status);
             bh_emit_kernel<<<std::min(GE, e.num_sms * 8), T, 0, s>>>(ba, P.owner, P.status);
             PubArgs pa{peers, lay.off_celltab, lay.off_workpub, nparts, plan2, er, part_id(r),
@@ -2183,6 +2117,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         ta.tcount = w.top.tcount; ta.tm3 = w.top.tm3; ta.tleaf = w.top.tleaf; ta.tchild = w.top.tchild;
         ta.blk = w.top.blk; ta.cblk = w.top.cblk;
         ta.top_off = static_cast<unsigned>(kMaxRanks) << kPartShift;
+        ta.q_scale = inv_theta2(theta);
         bh_top_build_kernel<<<1, 256, 0, s>>>(ta, w.status);
         e.ctr.kernel_launches++;
         tt.blk[kMaxRanks] = w.top.blk;
@@ -2192,7 +2127,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
         PhaseScope ps(e, 0);
         for (int r = 0; r < nlocal; r++) {
             PartBufs& P = w.parts[r];
-            launch_traverse(e, tt, P.sx, P.sy, P.gidx, nullptr, est, theta, w.status, real ? 0 : r, P.mkeys,
+            launch_traverse(e, tt, P.sx, P.sy, P.gidx, nullptr, est, w.status, real ? 0 : r, P.mkeys,
                             reinterpret_cast<unsigned*>(P.arena + lay.off_cellwork), &P.status->n_part, w.top.epoch_dev);
         }
     }
