@@ -2159,6 +2159,9 @@ static int choose_sort_levels(const BhStatus& h, int n) {
     int L = kLevels;
     while (L > 6 && tail[L - 1] * 32ull <= static_cast<unsigned long long>(n)) L--;
     if (L > 16 && tail[16] * 4ull <= static_cast<unsigned long long>(n)) L = 16;
+    // 12 levels = 24 key bits = one radix pass fewer.  Measured on B200 (profiles/r02_sort_depth_sweep.jsonl and the round-2 probes):
+    // a pass costs about 10 us + 8 us per million keys, the fix-up about 64 us per million neighbour pairs it has to order.
+    if (L > 12 && static_cast<double>(tail[12]) * 64e-6 < 10.0 + 8e-6 * static_cast<double>(n)) L = 12;
     if (getenv("NB_DEBUG_SORT"))
         fprintf(stderr, "nbody_b200: sort depth: n=%d tail[12]=%llu tail[14]=%llu tail[16]=%llu tail[18]=%llu tail[20]=%llu -> %d levels\n", n,
                 tail[12], tail[14], tail[16], tail[18], tail[20], L);
