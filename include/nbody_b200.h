@@ -135,6 +135,12 @@ int32_t nbx_set_async(int32_t enable);
 /* Seed for nb_random_disk / nb_stable_orbits. */
 void nbx_seed(uint64_t seed);
 
+/* Replaces the set with a Plummer model generated on the device (same counter-based RNG): scale radius a_scale,
+ * truncated at 10 a_scale, projected to z = 0, equal masses, isotropic Gaussian velocities with the local dispersion
+ * -- the synthetic cloud of BASELINE.json configurations 2-5.  The reference has no such generator (its two are
+ * nb_random_disk and nb_stable_orbits); like those it aborts on invalid arguments. */
+void nbx_plummer(int32_t num_particles, float a_scale, float mass_per_body);
+
 /* Kernel-level tuning knobs (0 = library default): bodies per thread of the all-pairs kernel,
  * target waves of work items, resident CTAs per SM. */
 int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_per_sm);

@@ -49,6 +49,7 @@ SYMBOLS = {
     "nbx_set_square_aabb": (i32, [i32]),
     "nbx_set_peer_timeout_ms": (i32, [i32]),
     "nbx_seed": (None, [u64]),
+    "nbx_plummer": (None, [i32, f32, f32]),
     "nbx_tune": (i32, [i32, i32, i32]),
     "nbx_get_counters": (None, [vp]),
     "nbx_reset_counters": (None, []),
@@ -207,6 +208,10 @@ class NBodyLib:
 
     def seed(self, s: int) -> None:
         self.L.nbx_seed(s)
+
+    def plummer(self, n: int, a_scale: float = 5.0, mass_per_body: float = 1e-2) -> None:
+        """Device-side Plummer set (projected to z = 0), the counterpart of ic.plummer_2d."""
+        self.L.nbx_plummer(n, a_scale, mass_per_body)
 
     def tune(self, bodies_per_thread: int = 0, target_waves: int = 0, ctas_per_sm: int = 0) -> None:
         self._chk(self.L.nbx_tune(bodies_per_thread, target_waves, ctas_per_sm), "nbx_tune")

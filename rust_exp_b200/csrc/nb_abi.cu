@@ -260,6 +260,16 @@ void nbx_seed(uint64_t seed) {
     engine().seed = seed;
 }
 
+// the Plummer set of configurations C2-C5 generated on the device (no reference counterpart)
+void nbx_plummer(int32_t num_particles, float a_scale, float mass_per_body) {
+    NB_LOCK();
+    Engine& e = engine();
+    if (!(a_scale > 0.f) || !(mass_per_body > 0.f)) fatal("nbx_plummer: scale and mass per body must be positive", __FILE__, __LINE__);
+    replace_set_begin(e, num_particles < 0 ? 0 : num_particles);
+    generate_plummer(e, e.n, a_scale, mass_per_body);
+    replace_set_end(e);
+}
+
 int32_t nbx_tune(int32_t bodies_per_thread, int32_t target_waves, int32_t ctas_per_sm) {
     NB_LOCK();
     Engine& e = engine();

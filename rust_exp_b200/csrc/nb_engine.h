@@ -249,6 +249,7 @@ void kdk_close(Engine& e);   // nb_engine.cu: apply the owed half kick (one forc
 void launch_fill_zero_f32(Engine& e, float* p, size_t n);
 void generate_random_disk(Engine& e, int n);
 void generate_stable_orbits(Engine& e, int n, float rmin, float rmax);
+void generate_plummer(Engine& e, int n, float a_scale, float mass_per_body);
 
 // nb_allpairs.cu
 void allpairs_slices(const Engine& e, int n_local, int L, int nseg, int* slice_len, int* per_seg);

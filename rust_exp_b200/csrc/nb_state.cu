@@ -264,7 +264,7 @@ __device__ __forceinline__ float u01(uint64_t seed, uint64_t idx, uint32_t strea
     return static_cast<float>(z >> 40) * (1.0f / 16777216.0f);
 }
 
-__global__ void gen_kernel(int kind, uint64_t seed, int begin, int count, int L, float rmin, float rmax,
+__global__ void gen_kernel(int kind, uint64_t seed, int begin, int count, int L, float n_total, float rmin, float rmax,
                            float* __restrict__ x0, float* __restrict__ y0, float* __restrict__ x1,
                            float* __restrict__ y1, float* __restrict__ m, float* __restrict__ vx,
                            float* __restrict__ vy) {
@@ -282,6 +282,27 @@ __global__ void gen_kernel(int kind, uint64_t seed, int begin, int count, int L,
             qx = -3.5f + 7.0f * u01(seed, gi, 2);
             qy = -3.5f + 7.0f * u01(seed, gi, 3);
             mm = 0.1f + 1.4f * u01(seed, gi, 4);
+        } else if (kind == 2) {
+            // nbx_plummer: Plummer model of scale a = rmin, equal masses rmax, truncated at 10 a, projected to z = 0
+            // (configurations C2-C5; the same construction as rust_exp_b200/ic.py::plummer_2d).
+            // Radius from the cumulative mass profile M(r)/M = r^3 / (r^2 + a^2)^(3/2); isotropic direction; velocities
+            // Gaussian (Box-Muller) with the local dispersion sqrt(N m / 6) (1 + r^2/a^2)^(-1/4).
+            const float a = rmin;
+            const float xmax = 1000.0f / (101.0f * sqrtf(101.0f));
+            const float u = fmaxf(u01(seed, gi, 0), 5.9604645e-8f) * xmax;
+            const float r = a * rsqrtf(powf(u, -2.0f / 3.0f) - 1.0f);
+            const float cz = 2.0f * u01(seed, gi, 1) - 1.0f;
+            const float ph = 2.0f * 3.14159265358979323846f * u01(seed, gi, 2);
+            const float sn = sqrtf(fmaxf(0.0f, 1.0f - cz * cz));
+            px = r * sn * cosf(ph);
+            py = r * sn * sinf(ph);
+            mm = rmax;
+            const float q = r / a;
+            const float sigma = sqrtf(n_total * mm / 6.0f) * rsqrtf(sqrtf(1.0f + q * q));
+            const float g = sqrtf(-2.0f * logf(fmaxf(u01(seed, gi, 3), 5.9604645e-8f)));
+            const float ga = 2.0f * 3.14159265358979323846f * u01(seed, gi, 4);
+            qx = sigma * g * cosf(ga);
+            qy = sigma * g * sinf(ga);
         } else {
             // nb_stable_orbits: rs-src/nbody.rs:85-103
             if (gi == 0) {
@@ -303,7 +324,7 @@ __global__ void gen_kernel(int kind, uint64_t seed, int begin, int count, int L,
 static void launch_gen(Engine& e, int kind, float rmin, float rmax) {
     const int L = static_cast<int>(e.lay.L);
     if (L == 0) return;
-    gen_kernel<<<(L + kBlk - 1) / kBlk, kBlk, 0, e.stream>>>(kind, e.seed, local_begin(e), local_count(e), L, rmin,
+    gen_kernel<<<(L + kBlk - 1) / kBlk, kBlk, 0, e.stream>>>(kind, e.seed, local_begin(e), local_count(e), L, static_cast<float>(e.n), rmin,
                                                             rmax, e.arena.x(e.lay, 0), e.arena.y(e.lay, 0),
                                                             e.arena.x(e.lay, 1), e.arena.y(e.lay, 1), e.arena.m(e.lay),
                                                             e.arena.vx(e.lay), e.arena.vy(e.lay));
@@ -313,5 +334,6 @@ static void launch_gen(Engine& e, int kind, float rmin, float rmax) {
 }
 void generate_random_disk(Engine& e, int n) { (void)n; launch_gen(e, 0, 0.f, 0.f); }
 void generate_stable_orbits(Engine& e, int n, float rmin, float rmax) { (void)n; launch_gen(e, 1, rmin, rmax); }
+void generate_plummer(Engine& e, int n, float a_scale, float mass_per_body) { (void)n; launch_gen(e, 2, a_scale, mass_per_body); }
 
 }  // namespace nb

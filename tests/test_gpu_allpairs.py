@@ -283,6 +283,31 @@ def test_generators_distribution_level(fresh):
     assert np.array_equal(bits(fresh.get_particles()), bits(d))  # seeded => reproducible
 
 
+def test_device_plummer_matches_the_host_generator_in_distribution(fresh):
+    """nbx_plummer against ic.plummer_2d: same radial profile, dispersion and masses."""
+    n = 200000
+    fresh.seed(7)
+    fresh.plummer(n, 5.0, 1e-2)
+    g = fresh.get_particles()
+    h = ic.plummer_2d(n, seed=7)
+    assert g.shape == (n, 5) and np.all(g[:, 4] == np.float32(1e-2)) and np.isfinite(g).all()
+    rg, rh = np.hypot(g[:, 0], g[:, 1]), np.hypot(h[:, 0], h[:, 1])
+    assert rg.max() <= 50.0 + 1e-3                       # truncated at 10 a
+    qs = [0.1, 0.25, 0.5, 0.75, 0.9, 0.99]
+    assert np.allclose(np.quantile(rg, qs), np.quantile(rh, qs), rtol=0.03)
+    assert abs(g[:, 0].mean()) < 0.05 and abs(g[:, 1].mean()) < 0.05          # isotropic
+    inner_g, inner_h = rg < 2.0, rh < 2.0
+    for c in (2, 3):
+        assert abs(g[:, c].mean()) < 0.05 * g[:, c].std()
+        assert np.isclose(g[inner_g, c].std(), h[inner_h, c].std(), rtol=0.05)
+        assert np.isclose(g[~inner_g, c].std(), h[~inner_h, c].std(), rtol=0.05)
+    fresh.seed(7)
+    fresh.plummer(n, 5.0, 1e-2)
+    assert np.array_equal(bits(fresh.get_particles()), bits(g))               # seeded => reproducible
+    fresh.step_barnes_hut(0.5, 0.01, 1)                                       # and it is a usable set
+    assert np.isfinite(fresh.get_particles()).all()
+
+
 def test_counters_report_kernel_launches(fresh):
     fresh.set_particles(ic.random_disk(2048, seed=1))
     fresh.reset_counters()

@@ -66,7 +66,7 @@ def main():
     lib.step_barnes_hut(0.5, 0.01, 1); lib.step_brute_force(0.01); lib.get_particles()
     lib.set_integrator(binding.INTEGRATOR_EULER); lib.set_square_aabb(False)
     done("opt-ins: leapfrog KDK closing kick, squared root box")
-    lib.random_disk(5000); lib.stable_orbits(5000, 0.5, 30.0)
+    lib.random_disk(5000); lib.stable_orbits(5000, 0.5, 30.0); lib.plummer(5000, 5.0, 1e-2)
     lib.draw(160, 120)
     done("device generators + nb_draw scatter")
     lib.configure3(binding.LAW3_NEWTON, 1e-4)
