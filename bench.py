@@ -280,7 +280,9 @@ class Ctx:
         names = [args.workload] + (bh_sub_workloads(self.world) if (args.workload == DEFAULT_WORKLOAD and not args.no_bh) else [])
         self.max_n = max(max(WORKLOADS[k]["n"] for k in names), 65536)
         if self.world > 1:
-            nbdist.wire(self.lib, self.max_n, {"p2p_direct": 0, "p2p_gather": 1, "nccl": 2}[args.transport])
+            # the sharded nbx3 extension exchanges positions with the library's own ncclAllGather: it needs the communicator
+            nbdist.wire(self.lib, self.max_n, {"p2p_direct": 0, "p2p_gather": 1, "nccl": 2}[args.transport],
+                        nccl=WORKLOADS[args.workload]["kind"] == "allpairs3")
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
         pk = peaks()
         self.pk = pk
@@ -308,8 +310,6 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
     w = WORKLOADS[name]
     n = w["n"]
     is3 = w["kind"] == "allpairs3"
-    if is3 and world > 1:
-        raise SystemExit("the nbx3 extension workloads are single-GPU")
     width = 7 if is3 else 5
     # pinned host state (the e2e leg copies from / to it every step)
     host = torch.empty((n, width), dtype=torch.float32, pin_memory=True)
@@ -411,8 +411,14 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
     torch.cuda.synchronize()
     e2e_s = cx.allreduce([time.perf_counter() - te0], "max")[0] / e2e_steps
     b, c = lib.dist_local_range() if world > 1 else (0, n)
+    if is3 and world > 1:   # rows of the nbx3 set: shards of ceil(n / 1024 / world) * 1024
+        shard = -(-(-(-n // 1024)) // world) * 1024
+        b = min(n, rank * shard)
+        c = min(n, b + shard) - b
     h2d = int(cx.allreduce([4 * width * c], "sum")[0])
     d2h = h2d
+    if is3 and world > 1:   # every rank uploads and reads back the whole nbx3 set
+        h2d = d2h = 4 * width * n * world
 
     fp32_peak, pk, sms, sm_max = cx.fp32_peak, cx.pk, cx.sms, cx.sm_max
     out = {"workload": f"{name}: {w['desc']}", "n_bodies": n, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,

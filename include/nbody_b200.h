@@ -201,14 +201,19 @@ int32_t nbx_bh_accelerations(float theta, float *axy_out, int32_t n);
  * A separate particle set of 7-float records {px,py,pz,vx,vy,vz,m} and an all-pairs step with a selectable
  * pair law.  LAW_NEWTON: a_i = sum m_j d/(|d|^2+eps2)^(3/2) (rsqrt-based, 20 flop/pair -- the kernel the
  * project brief describes).  LAW_REF: the reference's un-normalised law m_j d/(|d|^2+eps2) lifted to 3-D; with
- * z == 0 it reproduces the 2-D FAST kernel bit for bit.  Single GPU.  Integrator as in the reference
- * (rs-src/nbody.rs:153-160).  Default: LAW_NEWTON, eps2 = 1e-4. */
+ * z == 0 it reproduces the 2-D FAST kernel bit for bit.  Integrator as in the reference
+ * (rs-src/nbody.rs:153-160).  Default: LAW_NEWTON, eps2 = 1e-4.
+ * Multi-GPU: once the process group is wired WITH the NCCL communicator (nbx_dist_init + nbx_dist_nccl_init), the rows
+ * shard by index -- every rank keeps all positions, evaluates and integrates its own rows and one in-place
+ * ncclAllGather per coordinate exchanges the new positions (all nbx3_* calls are then collective).  The result equals
+ * the single-GPU result bit for bit.  nbx3_set_sharded(0) makes every rank compute every row instead (default 1). */
 #define NBX3_LAW_NEWTON 0
 #define NBX3_LAW_REF 1
 int32_t nbx3_num_particles(void);
 int32_t nbx3_set_particles(const float *aos7, int32_t n);
 int32_t nbx3_get_particles(float *aos7_out, int32_t n);
 int32_t nbx3_configure(int32_t law, float eps2);
+int32_t nbx3_set_sharded(int32_t on);
 int32_t nbx3_step_all_pairs(float dt);
 int32_t nbx3_accelerations(float *axyz_out, int32_t n);
 

@@ -66,6 +66,7 @@ SYMBOLS = {
     "nbx3_set_particles": (i32, [vp, i32]),
     "nbx3_get_particles": (i32, [vp, i32]),
     "nbx3_configure": (i32, [i32, f32]),
+    "nbx3_set_sharded": (i32, [i32]),
     "nbx3_step_all_pairs": (i32, [f32]),
     "nbx3_accelerations": (i32, [vp, i32]),
     "nbx_dist_init": (i32, [i32, i32, i32]),
@@ -282,6 +283,9 @@ class NBodyLib:
 
     def configure3(self, law: int, eps2: float = 1e-4) -> None:
         self._chk(self.L.nbx3_configure(law, eps2), "nbx3_configure")
+
+    def set_sharded3(self, on: bool) -> None:
+        self._chk(self.L.nbx3_set_sharded(1 if on else 0), "nbx3_set_sharded")
 
     def step3(self, dt: float) -> None:
         self._chk(self.L.nbx3_step_all_pairs(dt), "nbx3_step_all_pairs")

@@ -11,6 +11,8 @@
 // Same structure as allpairs_fast_kernel: persistent CTAs, a producer warp bulk-TMA-streaming x|y|z|m tiles
 // through an mbarrier ring, consumers on broadcast LDS.128 + packed FP32, deterministic per-slice partials.
 // Integrator: the reference's semi-implicit Euler (v += dt*a ; p += dt*v), rs-src/nbody.rs:153-160.
+#include <algorithm>
+
 #include "nb_engine.h"
 
 namespace nb {
@@ -34,6 +36,7 @@ struct Args3 {
     int slice_len, nslices;
     float eps2;
     float4* partial;              // [nslices][n_pad] (ax, ay, az, -)
+    int itile_begin, n_itiles;    // the i tiles this launch evaluates (all of them, or this rank's rows when sharded)
 };
 
 template <int LAW>
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(k3Threads, 3) allpairs3_kernel(const Args3 a) 
         mbar_fence_init();
     }
     __syncthreads();
-    const int n_itiles = (a.n + k3TI - 1) / k3TI;
+    const int n_itiles = a.n_itiles;
     const int n_items = n_itiles * a.nslices;
     if (warp == k3Warps) {
         if (lane == 0) {
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(k3Threads, 3) allpairs3_kernel(const Args3 a) 
     const float2 eps = make_float2(a.eps2, a.eps2);
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int sl = item / n_itiles, itile = item - sl * n_itiles;
+        const int sl = item / n_itiles, itile = a.itile_begin + (item - sl * n_itiles);
         const int j0 = sl * a.slice_len, j1 = min(j0 + a.slice_len, a.n_pad);
         const int ntiles = (j1 - j0) / k3TJ;
         float nxi[k3I], nyi[k3I], nzi[k3I];
@@ -131,10 +134,11 @@ __global__ void __launch_bounds__(k3Threads, 3) allpairs3_kernel(const Args3 a) 
     }
 }
 
-__global__ void integrate3_kernel(const float4* __restrict__ partial, int nslices, int n_pad, int n, float dt, int update,
+// rows [i_begin, i_end) only (this rank's rows when sharded)
+__global__ void integrate3_kernel(const float4* __restrict__ partial, int nslices, int n_pad, int i_begin, int i_end, float dt, int update,
                                   float* x, float* y, float* z, float* vx, float* vy, float* vz, float* acc_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int i = i_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i_end) return;
     float ax = 0.f, ay = 0.f, az = 0.f;
     for (int s = 0; s < nslices; s++) {
         const float4 p = partial[static_cast<size_t>(s) * n_pad + i];
@@ -164,8 +168,15 @@ __global__ void soa_to_aos7_kernel(float* __restrict__ aos, int n, const float* 
     r[0] = x[i]; r[1] = y[i]; r[2] = z[i]; r[3] = vx[i]; r[4] = vy[i]; r[5] = vz[i]; r[6] = m[i];
 }
 
+// Sharding (round 2): with the process group wired (nbx_dist_init + nbx_dist_nccl_init) every rank keeps the whole
+// position set, evaluates and integrates only its own rows [rank * shard, (rank + 1) * shard) and the new positions
+// are exchanged with one in-place ncclAllGather per coordinate -- the "index shards + per-step NCCL all-gather of
+// positions" the project brief describes.  The j-slice plan stays the single-GPU one, so the sharded result equals
+// the single-GPU result bit for bit.  Velocities stay with their rows and are gathered by nbx3_get_particles.
 struct State3 {
     int n = 0, n_pad = 0, cap = 0;
+    int shard = 0;                 // rows per rank when sharded (multiple of 1024), else 0
+    bool want_shard = true;
     float* buf = nullptr;          // 7 arrays of cap floats
     float4* partial = nullptr;
     size_t partial_cap = 0;
@@ -190,21 +201,41 @@ static void stage3(Engine& e, State3& s, size_t floats) {
     }
 }
 
+static bool sharded3(const Engine& e, const State3& s) { return s.want_shard && e.dist && e.world > 1 && dist_nccl_ready(); }
+
+void x3_set_sharded(Engine& e, int on) {
+    State3& s = st3(e);
+    if (e.dist && e.world > 1 && s.shard > 0 && !on) {
+        // leaving sharded mode: every rank needs every velocity from here on
+        float* v[3] = {s.arr(3), s.arr(4), s.arr(5)};
+        dist_nccl_allgather_inplace(e, v, 3, static_cast<size_t>(s.shard));
+        s.shard = 0;
+    }
+    s.want_shard = on != 0;
+    if (s.want_shard && s.n_pad > 0 && sharded3(e, s)) {
+        const int shard = ((s.n_pad / 1024 + e.world - 1) / e.world) * 1024;
+        if (static_cast<long long>(shard) * e.world <= s.cap) s.shard = shard;   // else: takes effect at the next nbx3_set_particles
+    }
+}
+
 void x3_set(Engine& e, const float* aos7, int n) {
     State3& s = st3(e);
     if (n < 0) n = 0;
     const int n_pad = ((n + 1023) / 1024) * 1024 + (n == 0 ? 1024 : 0);
-    if (n_pad > s.cap) {
+    // sharded: the arrays are the receive buffers of the all-gather, world * shard long (>= n_pad)
+    const int shard = sharded3(e, s) ? ((n_pad / 1024 + e.world - 1) / e.world) * 1024 : 0;
+    const int n_alloc = shard ? shard * e.world : n_pad;
+    if (n_alloc > s.cap) {
         NB_CUDA(cudaStreamSynchronize(e.stream));
         if (s.buf) NB_CUDA(cudaFree(s.buf));
-        NB_CUDA(cudaMalloc(&s.buf, 7 * sizeof(float) * static_cast<size_t>(n_pad)));
-        s.cap = n_pad;
+        NB_CUDA(cudaMalloc(&s.buf, 7 * sizeof(float) * static_cast<size_t>(n_alloc)));
+        s.cap = n_alloc;
     }
-    s.n = n; s.n_pad = n_pad;
+    s.n = n; s.n_pad = n_pad; s.shard = shard;
     stage3(e, s, 7 * static_cast<size_t>(n > 0 ? n : 1));
     if (n > 0) NB_CUDA(cudaMemcpyAsync(s.stage, aos7, 7 * sizeof(float) * static_cast<size_t>(n), cudaMemcpyHostToDevice, e.stream));
-    aos7_to_soa_kernel<<<(n_pad + 255) / 256, 256, 0, e.stream>>>(s.stage, n, n_pad, s.arr(0), s.arr(1), s.arr(2), s.arr(3), s.arr(4),
-                                                               s.arr(5), s.arr(6));
+    aos7_to_soa_kernel<<<(n_alloc + 255) / 256, 256, 0, e.stream>>>(s.stage, n, n_alloc, s.arr(0), s.arr(1), s.arr(2), s.arr(3), s.arr(4),
+                                                                 s.arr(5), s.arr(6));
     NB_CUDA(cudaGetLastError());
     e.ctr.kernel_launches++;
 }
@@ -213,6 +244,10 @@ void x3_get(Engine& e, float* aos7, int n) {
     State3& s = st3(e);
     if (n > s.n) n = s.n;
     if (n <= 0) return;
+    if (s.shard) {   // velocities live with their rows: collect them (collective call)
+        float* v[3] = {s.arr(3), s.arr(4), s.arr(5)};
+        dist_nccl_allgather_inplace(e, v, 3, static_cast<size_t>(s.shard));
+    }
     stage3(e, s, 7 * static_cast<size_t>(n));
     soa_to_aos7_kernel<<<(n + 255) / 256, 256, 0, e.stream>>>(s.stage, n, s.arr(0), s.arr(1), s.arr(2), s.arr(3), s.arr(4), s.arr(5), s.arr(6));
     NB_CUDA(cudaGetLastError());
@@ -235,7 +270,14 @@ void x3_step(Engine& e, float dt, int update, float* acc_host) {
         attr_set = true;
     }
     // the 2-D kernel's own decomposition rule, so that <3,REF> with z = 0 groups its sums exactly like it
-    const int n_itiles = (s.n + k3TI - 1) / k3TI;
+    // (always the plan of the whole set: a sharded step then adds up exactly what the single-GPU step adds up)
+    int i_begin = 0, i_end = s.n;
+    if (s.shard) {
+        i_begin = std::min(s.n, e.rank * s.shard);
+        i_end = std::min(s.n, i_begin + s.shard);
+    }
+    const int itile_begin = i_begin / k3TI;               // shard is a multiple of 1024
+    const int n_itiles = i_end > i_begin ? (i_end + k3TI - 1) / k3TI - itile_begin : 0;
     int slice_len = 0, per = 1;
     allpairs_slices(e, s.n, s.n_pad, 1, &slice_len, &per);
     const size_t need = static_cast<size_t>(per) * s.n_pad;
@@ -245,19 +287,31 @@ void x3_step(Engine& e, float dt, int update, float* acc_host) {
         NB_CUDA(cudaMalloc(&s.partial, need * sizeof(float4)));
         s.partial_cap = need;
     }
-    Args3 a{s.arr(0), s.arr(1), s.arr(2), s.arr(6), s.n, s.n_pad, slice_len, per, s.eps2, s.partial};
+    Args3 a{s.arr(0), s.arr(1), s.arr(2), s.arr(6), s.n, s.n_pad, slice_len, per, s.eps2, s.partial, itile_begin, n_itiles};
     int grid = e.num_sms * 3;
     if (grid > n_itiles * per) grid = n_itiles * per;
-    if (s.law == NBX3_LAW_NEWTON) allpairs3_kernel<NBX3_LAW_NEWTON><<<grid, k3Threads, sizeof(Smem3), e.stream>>>(a);
-    else allpairs3_kernel<NBX3_LAW_REF><<<grid, k3Threads, sizeof(Smem3), e.stream>>>(a);
-    NB_CUDA(cudaGetLastError());
+    if (grid > 0) {
+        if (s.law == NBX3_LAW_NEWTON) allpairs3_kernel<NBX3_LAW_NEWTON><<<grid, k3Threads, sizeof(Smem3), e.stream>>>(a);
+        else allpairs3_kernel<NBX3_LAW_REF><<<grid, k3Threads, sizeof(Smem3), e.stream>>>(a);
+        NB_CUDA(cudaGetLastError());
+        e.ctr.kernel_launches++;
+    }
     float* acc_dev = nullptr;
-    if (acc_host) { stage3(e, s, 7 * static_cast<size_t>(s.n)); acc_dev = s.stage; }
-    integrate3_kernel<<<(s.n + 255) / 256, 256, 0, e.stream>>>(s.partial, per, s.n_pad, s.n, dt, update, s.arr(0), s.arr(1), s.arr(2), s.arr(3),
-                                                              s.arr(4), s.arr(5), acc_dev);
-    NB_CUDA(cudaGetLastError());
-    e.ctr.kernel_launches += 2;
-    e.ctr.allpairs_pairs += static_cast<uint64_t>(s.n) * static_cast<uint64_t>(s.n - 1);
+    if (acc_host) { stage3(e, s, 3 * static_cast<size_t>(s.shard ? s.shard * e.world : s.n) + 4); acc_dev = s.stage; }
+    if (i_end > i_begin) {
+        integrate3_kernel<<<(i_end - i_begin + 255) / 256, 256, 0, e.stream>>>(s.partial, per, s.n_pad, i_begin, i_end, dt, update, s.arr(0),
+                                                                               s.arr(1), s.arr(2), s.arr(3), s.arr(4), s.arr(5), acc_dev);
+        NB_CUDA(cudaGetLastError());
+        e.ctr.kernel_launches++;
+    }
+    e.ctr.allpairs_pairs += static_cast<uint64_t>(i_end - i_begin) * static_cast<uint64_t>(s.n - 1);
+    if (s.shard) {
+        if (update) {   // the new positions of every rank's rows, in place
+            float* pos[3] = {s.arr(0), s.arr(1), s.arr(2)};
+            dist_nccl_allgather_inplace(e, pos, 3, static_cast<size_t>(s.shard));
+        }
+        if (acc_dev) dist_nccl_allgather_inplace(e, &acc_dev, 1, 3 * static_cast<size_t>(s.shard));   // rows are 3 floats, shards contiguous
+    }
     if (acc_host) {
         NB_CUDA(cudaMemcpyAsync(acc_host, acc_dev, 3 * sizeof(float) * static_cast<size_t>(s.n), cudaMemcpyDeviceToHost, e.stream));
         NB_CUDA(cudaStreamSynchronize(e.stream));

@@ -414,6 +414,13 @@ int32_t nbx3_configure(int32_t law, float eps2) {
     x3_config(e, law, eps2);
     return 0;
 }
+int32_t nbx3_set_sharded(int32_t on) {
+    NB_LOCK();
+    Engine& e = engine();
+    ensure_init(e);
+    x3_set_sharded(e, on);
+    return 0;
+}
 int32_t nbx3_step_all_pairs(float dt) {
     NB_LOCK();
     Engine& e = engine();

@@ -349,6 +349,21 @@ int dist_import(Engine& e, const void* all, int world) {
     return 0;
 }
 
+bool dist_nccl_ready() {
+    Nccl* n = nccl_load();
+    return n && n->comm;
+}
+
+// In-place ncclAllGather of `nbufs` arrays on the library stream: rank r contributes bufs[k][r * count .. (r + 1) * count).
+void dist_nccl_allgather_inplace(Engine& e, float* const* bufs, int nbufs, size_t count) {
+    Nccl* n = nccl_load();
+    if (!n || !n->comm) fatal("this path needs the NCCL communicator (nbx_dist_nccl_init was not called)", __FILE__, __LINE__);
+    n->GroupStart();
+    for (int k = 0; k < nbufs; k++) n->AllGather(bufs[k] + static_cast<size_t>(e.rank) * count, bufs[k], count, ncclFloat32, n->comm, e.stream);
+    const ncclResult_t r = n->GroupEnd();
+    if (r != 0) fatal(n->GetErrorString ? n->GetErrorString(r) : "ncclAllGather failed", __FILE__, __LINE__);
+}
+
 int dist_nccl_unique_id(void* out128) {
     Nccl* n = nccl_load();
     if (!n) return -1;

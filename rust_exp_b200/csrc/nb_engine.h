@@ -270,6 +270,8 @@ int dist_init(Engine& e, int rank, int world, int max_particles);
 int dist_export(Engine& e, void* out64);
 int dist_import(Engine& e, const void* all, int world);
 int dist_nccl_unique_id(void* out128);
+bool dist_nccl_ready();
+void dist_nccl_allgather_inplace(Engine& e, float* const* bufs, int nbufs, size_t count);
 int dist_nccl_init(Engine& e, const void* id128);
 
 // nb_bh.cu
@@ -286,6 +288,7 @@ void x3_set(Engine& e, const float* aos7, int n);
 void x3_get(Engine& e, float* aos7, int n);
 int x3_num(Engine& e);
 void x3_config(Engine& e, int law, float eps2);
+void x3_set_sharded(Engine& e, int on);
 void x3_step(Engine& e, float dt, int update, float* acc_host);
 void x3_shutdown(Engine& e);
 

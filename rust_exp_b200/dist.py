@@ -126,8 +126,10 @@ def broadcast_bytes(payload: bytes | None, src: int = 0, group=None) -> bytes:
     return box[0]
 
 
-def wire(lib, max_particles: int, transport: int = 0, group=None) -> ShardLayout:
-    """Collective: allocate + exchange the symmetric arenas of all ranks and (optionally) set up NCCL."""
+def wire(lib, max_particles: int, transport: int = 0, group=None, nccl: bool = False) -> ShardLayout:
+    """Collective: allocate + exchange the symmetric arenas of all ranks and (optionally) set up NCCL.
+
+    nccl=True creates the library's NCCL communicator whatever the transport (the sharded nbx3_* path needs it)."""
     import torch.distributed as dist
 
     from .binding import TRANSPORT_NCCL
@@ -136,7 +138,7 @@ def wire(lib, max_particles: int, transport: int = 0, group=None) -> ShardLayout
     lib.dist_init(rank, world, max_particles)
     handles = all_gather_bytes(lib.dist_export(), group)
     lib.dist_import(b"".join(handles), world)
-    if transport == TRANSPORT_NCCL:
+    if transport == TRANSPORT_NCCL or nccl:
         uid = lib.dist_nccl_unique_id() if rank == 0 else None
         uid = broadcast_bytes(uid, 0, group)
         lib.dist_nccl_init(uid)

@@ -141,6 +141,34 @@ def main():
     report("bh_partitioned_5_steps_vs_oracle", err <= 1e-4, rel_pos_err=err)
     lib.bh_count_interactions(False)
 
+    # ---- nbx3 extension sharded by rows (ncclAllGather of the positions) == every rank computing every row, bit for bit ----
+    for n3, law in ((5000, binding.LAW3_NEWTON), (20000, binding.LAW3_REF)):
+        s3 = ic.plummer_3d(n3, seed=46)
+        lib.configure3(law, 1e-4)
+        res = {}
+        for sharded in (False, True):
+            lib.set_sharded3(sharded)
+            lib.set_particles3(s3)
+            a3 = lib.accelerations3()
+            for _ in range(4):
+                lib.step3(0.01)
+            res[sharded] = (a3, lib.get_particles3())
+        same = np.array_equal(bits(res[True][0]), bits(res[False][0])) and np.array_equal(bits(res[True][1]), bits(res[False][1]))
+        every = [None] * world
+        dist.all_gather_object(every, bits(res[True][1]).tobytes())
+        # and against an f64 evaluation of the same law
+        p = s3[:, :3].astype(np.float64); mm = s3[:, 6].astype(np.float64)
+        ref = np.zeros((n3, 3))
+        for i0 in range(0, n3, 1000):
+            d = p[None, :, :] - p[i0:i0 + 1000, None, :]
+            d2 = (d * d).sum(-1) + 1e-4
+            wgt = mm[None, :] / (d2 ** 1.5 if law == binding.LAW3_NEWTON else d2)
+            ref[i0:i0 + 1000] = (wgt[:, :, None] * d).sum(1)
+        err = float(np.abs(res[True][0] - ref).max() / np.abs(ref).max())
+        report(f"nbx3_sharded_n{n3}_law{law}", same and all(b == every[0] for b in every) and err <= 2e-5 and np.isfinite(res[True][1]).all(),
+               acc_err_vs_f64=err)
+    lib.set_sharded3(True)
+
     # ---- device-side generators when sharded: counter-based RNG keyed by the GLOBAL body index ----------
     lib.seed(77)
     lib.stable_orbits(50000, 0.5, 30.0)
