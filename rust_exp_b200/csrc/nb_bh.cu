@@ -839,7 +839,9 @@ __device__ __forceinline__ unsigned test_child(float q, float e, unsigned in_mas
         : "+f"(c), "=r"(open) : "f"(q), "f"(e), "r"(in_mask));
     return open;
 }
-template <bool COUNT, bool PARTS, int MINB>
+// EARLYC: when the child-block indices of the popped block are fetched.  0 = only if something is pushed (a second,
+// dependent load); 1 = together with the block, into registers; 2 = L1 prefetch issued with the block's loads.
+template <bool COUNT, bool PARTS, int MINB, int EARLYC>
 __global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
     const float* __restrict__ sy, const int* __restrict__ idx_sorted, const int* __restrict__ mine, int n_list,
@@ -887,6 +889,10 @@ __global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel
                 nb4 = tt.blk[0] + 4 * static_cast<size_t>(bi);
             }
             const float4 X = __ldg(nb4 + 0), Y = __ldg(nb4 + 1), M = __ldg(nb4 + 2), Q = __ldg(nb4 + 3);
+            const int4* __restrict__ cptr = (PARTS ? tt.cblk[part] : tt.cblk[0]) + bi;
+            int4 C = make_int4(0, 0, 0, 0);
+            if (EARLYC == 1) C = __ldg(cptr);
+            if (EARLYC == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(cptr));
             const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
             const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
             // d^2 + EPS: the denominator of the force law (rs-src/nbody.rs:180) and the right-hand side of the opening test
@@ -908,7 +914,7 @@ __global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel
             }
             if (PARTS) my_pops++;
             if (o0 | o1 | o2 | o3) {
-                const int4 C = __ldg((PARTS ? tt.cblk[part] : tt.cblk[0]) + bi);
+                if (EARLYC != 1) C = __ldg(cptr);
                 // stack order bottom -> top: child 3, 2, 1, 0 (non-empty masks only), so that child 0 is opened first
                 stack_push_if(sa, static_cast<unsigned>(C.w), o3);
                 stack_push_if(sa, static_cast<unsigned>(C.z), o2);
@@ -1157,9 +1163,9 @@ static int traverse_resident_blocks(Engine& e) {
     static int per_sm = 0;
     if (!per_sm) {
         const int mb = walk_minb();
-        if (mb == 5) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 5>, kTravWarps * 32, 0));
-        else if (mb == 7) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 7>, kTravWarps * 32, 0));
-        else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 6>, kTravWarps * 32, 0));
+        if (mb == 5) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 5, 0>, kTravWarps * 32, 0));
+        else if (mb == 7) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 7, 0>, kTravWarps * 32, 0));
+        else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 6, 0>, kTravWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
         if (const char* v = getenv("NB_BH_WALK_BLOCKS")) { const int c = atoi(v); if (c >= 1 && c < per_sm) per_sm = c; }   // experiments
     }
@@ -1176,8 +1182,9 @@ static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, con
     const int blocks = std::min(want, traverse_resident_blocks(e));
     const bool parts = tt.shift != 31;
     const int mb = walk_minb();
-#define NB_TRAV(C, P, B) bh_traverse_fast_kernel<C, P, B><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
-#define NB_TRAV2(C, P) do { if (mb == 5) NB_TRAV(C, P, 5); else if (mb == 7) NB_TRAV(C, P, 7); else NB_TRAV(C, P, 6); } while (0)
+    static const int earlyc = [] { const char* v = getenv("NB_BH_EARLYC"); const int c = v ? atoi(v) : 0; return (c == 1 || c == 2) ? c : 0; }();
+#define NB_TRAV(C, P, B, E) bh_traverse_fast_kernel<C, P, B, E><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
+#define NB_TRAV2(C, P) do { if (mb == 5) NB_TRAV(C, P, 5, 0); else if (mb == 7) NB_TRAV(C, P, 7, 0); else if (earlyc == 1) NB_TRAV(C, P, 6, 1); else if (earlyc == 2) NB_TRAV(C, P, 6, 2); else NB_TRAV(C, P, 6, 0); } while (0)
     if (e.bh_count) { if (parts) NB_TRAV2(true, true); else NB_TRAV2(true, false); }
     else { if (parts) NB_TRAV2(false, true); else NB_TRAV2(false, false); }
 #undef NB_TRAV2
