@@ -612,9 +612,10 @@ __global__ void bh_owner_kernel(const BuildArgs a, int* __restrict__ owner, BhSt
         const int dlo = i > 0 ? static_cast<int>(a.dcap[i - 1]) : -1;
         const int b = a.base[i];
         for (int k = 0; k < dhi - dlo && b + k < a.cap_interior; k++) owner[b + k] = i;
-        if (a.cut_level > 0) {
-            const int deep = dhi - max(dlo, a.cut_level - 1);
-            if (deep > 0) atomicAdd(&st->n_deep, deep);
+        if (a.cut_level > 0) {   // (the grid is a multiple of the warp size and n is uniform: whole warps get here together or not at all)
+            const int deep = max(0, dhi - max(dlo, a.cut_level - 1));
+            const int wsum = __reduce_add_sync(__activemask(), deep);
+            if (wsum > 0 && (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&st->n_deep, wsum);
         }
         if (i == 0) {
             const int total = a.base[n - 1];   // count[n-1] == 0
@@ -840,7 +841,8 @@ __device__ __forceinline__ unsigned test_child(float q, float e, unsigned in_mas
     return open;
 }
 // EARLYC: when the child-block indices of the popped block are fetched.  0 = only if something is pushed (a second,
-// dependent load); 1 = together with the block, into registers; 2 = L1 prefetch issued with the block's loads.
+// dependent load); 1 = together with the block, into registers (default: 1-2.5 % faster, gpurun r03d; an L1 prefetch
+// instead was 3 % slower).  NB_BH_EARLYC=0 selects the former for A/B runs.
 template <bool COUNT, bool PARTS, int MINB, int EARLYC>
 __global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel(
     const TreeTable tt, const float* __restrict__ sx,
@@ -892,7 +894,6 @@ __global__ void __launch_bounds__(kTravWarps * 32, MINB) bh_traverse_fast_kernel
             const int4* __restrict__ cptr = (PARTS ? tt.cblk[part] : tt.cblk[0]) + bi;
             int4 C = make_int4(0, 0, 0, 0);
             if (EARLYC == 1) C = __ldg(cptr);
-            if (EARLYC == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(cptr));
             const float2 dx01 = __fadd2_rn(make_float2(X.x, X.y), npx), dx23 = __fadd2_rn(make_float2(X.z, X.w), npx);
             const float2 dy01 = __fadd2_rn(make_float2(Y.x, Y.y), npy), dy23 = __fadd2_rn(make_float2(Y.z, Y.w), npy);
             // d^2 + EPS: the denominator of the force law (rs-src/nbody.rs:180) and the right-hand side of the opening test
@@ -1165,7 +1166,7 @@ static int traverse_resident_blocks(Engine& e) {
         const int mb = walk_minb();
         if (mb == 5) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 5, 0>, kTravWarps * 32, 0));
         else if (mb == 7) NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 7, 0>, kTravWarps * 32, 0));
-        else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 6, 0>, kTravWarps * 32, 0));
+        else NB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bh_traverse_fast_kernel<false, false, 6, 1>, kTravWarps * 32, 0));
         if (per_sm < 1) per_sm = 1;
         if (const char* v = getenv("NB_BH_WALK_BLOCKS")) { const int c = atoi(v); if (c >= 1 && c < per_sm) per_sm = c; }   // experiments
     }
@@ -1182,9 +1183,9 @@ static void launch_traverse(Engine& e, const TreeTable& tt, const float* sx, con
     const int blocks = std::min(want, traverse_resident_blocks(e));
     const bool parts = tt.shift != 31;
     const int mb = walk_minb();
-    static const int earlyc = [] { const char* v = getenv("NB_BH_EARLYC"); const int c = v ? atoi(v) : 0; return (c == 1 || c == 2) ? c : 0; }();
+    static const int earlyc = [] { const char* v = getenv("NB_BH_EARLYC"); return (v && atoi(v) == 0) ? 0 : 1; }();
 #define NB_TRAV(C, P, B, E) bh_traverse_fast_kernel<C, P, B, E><<<blocks, kTravWarps * 32, 0, e.stream>>>(tt, sx, sy, idx_sorted, mine, n_list, st, ticket_slot, keys_sorted, cell_work, n_dev, epoch_dev)
-#define NB_TRAV2(C, P) do { if (mb == 5) NB_TRAV(C, P, 5, 0); else if (mb == 7) NB_TRAV(C, P, 7, 0); else if (earlyc == 1) NB_TRAV(C, P, 6, 1); else if (earlyc == 2) NB_TRAV(C, P, 6, 2); else NB_TRAV(C, P, 6, 0); } while (0)
+#define NB_TRAV2(C, P) do { if (mb == 5) NB_TRAV(C, P, 5, 0); else if (mb == 7) NB_TRAV(C, P, 7, 0); else if (earlyc == 1) NB_TRAV(C, P, 6, 1); else NB_TRAV(C, P, 6, 0); } while (0)
     if (e.bh_count) { if (parts) NB_TRAV2(true, true); else NB_TRAV2(true, false); }
     else { if (parts) NB_TRAV2(false, true); else NB_TRAV2(false, false); }
 #undef NB_TRAV2
