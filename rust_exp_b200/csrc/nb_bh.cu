@@ -1525,6 +1525,25 @@ __global__ void bhp_boxes_reduce_kernel(const char* arena, size_t off_aabb, size
     }
 }
 
+// Warp-cooperative 32-ary search: first index in [lo, hi) at which the monotone predicate (false..false true..true) holds,
+// hi if none.  Every lane probes one position and a ballot narrows the range 32-fold per round: 4 dependent rounds for a
+// 524,288-element run where a per-thread bisection needs 19.  The whole warp must call it; the result is warp-uniform.
+template <typename Pred>
+__device__ __forceinline__ int warp_first_true(int lo, int hi, const int lane, Pred pred) {
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) >> 5;                 // >= 2
+        const int p = min(hi - 1, lo + (lane + 1) * step - 1);
+        const unsigned m = __ballot_sync(0xffffffffu, pred(p));
+        if (m == 0u) return hi;                               // lane 31 probed hi - 1
+        const int f = __ffs(m) - 1;
+        hi = min(hi - 1, lo + (f + 1) * step - 1) + 1;        // the probe of lane f is true: the answer is at or before it
+        lo = lo + f * step;                                   // the probe of lane f - 1 (lo + f*step - 1) was false
+    }
+    const int p = lo + lane;
+    const unsigned m = __ballot_sync(0xffffffffu, p < hi && pred(p));
+    return m ? lo + __ffs(m) - 1 : hi;
+}
+
 // ---- send: the key-sorted shard -> the inbox regions of the parts that own its cells --------------------------------
 struct SendArgs {
     const unsigned long long* keys;   // full keys of the shard (unsorted); the key of sorted position i is keys[order[i]]
@@ -1539,13 +1558,15 @@ struct SendArgs {
 };
 __global__ void __launch_bounds__(256) bhp_send_kernel(const SendArgs a) {
     __shared__ int lo[kMaxRanks + 1];
-    if (threadIdx.x <= a.nparts) {
-        // first sorted body whose cut-level cell is >= cut[p]: the start of part p's run
+    {   // first sorted body whose cut-level cell is >= cut[p]: the start of part p's run.  One warp per boundary (every CTA
+        // repeats this prologue, so it is kept to a few dependent rounds: it was half of this kernel's time as a bisection)
         const PartPlan* plan = a.plan2 + (a.er.get() & 1u);
-        const unsigned long long kmin = static_cast<unsigned long long>(plan->cut[threadIdx.x]) << kCellShift;
-        int l = 0, h = a.n_local;
-        while (l < h) { const int mid = (l + h) >> 1; if (a.keys[a.order[mid]] < kmin) l = mid + 1; else h = mid; }
-        lo[threadIdx.x] = l;
+        const int lane = threadIdx.x & 31;
+        for (int p = threadIdx.x >> 5; p <= a.nparts; p += blockDim.x >> 5) {
+            const unsigned long long kmin = static_cast<unsigned long long>(plan->cut[p]) << kCellShift;
+            const int l = warp_first_true(0, a.n_local, lane, [&](int i) { return a.keys[a.order[i]] >= kmin; });
+            if (lane == 0) lo[p] = l;
+        }
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < a.nparts)
@@ -1605,17 +1626,17 @@ __global__ void __launch_bounds__(256) bhp_merge_kernel(const MergeArgs a) {
             }
         }
         __syncthreads();
-        if (threadIdx.x < a.nparts) {
-            unsigned long long kmin = ~0ull, kmax = 0ull;
-            for (int r = 0; r < a.nparts; r++) { kmin = min(kmin, rmin[r]); kmax = max(kmax, rmax[r]); }
-            const int r = threadIdx.x;
-            const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
-            int l = 0, h = cnt[r];
-            while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] < kmin) l = mid + 1; else h = mid; }
-            wlo[r] = l;
-            h = cnt[r];   // the upper end is at or after the lower one
-            while (l < h) { const int mid = (l + h) >> 1; if (kr[mid] <= kmax) l = mid + 1; else h = mid; }
-            whi[r] = l;
+        {   // one warp per run (kMaxRanks == warps per CTA), 32-ary searches: this phase was 40 % of the kernel as 8 bisecting threads
+            static_assert(kMaxRanks <= 8, "one warp of the 256-thread CTA per run");
+            const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (r < a.nparts) {
+                unsigned long long kmin = ~0ull, kmax = 0ull;
+                for (int q = 0; q < a.nparts; q++) { kmin = min(kmin, rmin[q]); kmax = max(kmax, rmax[q]); }
+                const unsigned long long* kr = keys + static_cast<size_t>(r) * a.R;
+                const int l = warp_first_true(0, cnt[r], lane, [&](int i) { return kr[i] >= kmin; });
+                const int h = warp_first_true(l, cnt[r], lane, [&](int i) { return kr[i] > kmax; });   // at or after the lower end
+                if (lane == 0) { wlo[r] = l; whi[r] = h; }
+            }
         }
         __syncthreads();
         const int t = t0 + threadIdx.x;
@@ -1657,25 +1678,25 @@ struct PubArgs {
     int part;
     const unsigned* cellwork2;   // [2][cells]: this rank's measured walk cost per cell; last step's is parity (epoch + 1) & 1
 };
-__global__ void bh_celltab_kernel(const BuildArgs a, const PubArgs pub) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one WARP per cut-level cell (its body range by two 32-ary searches; lane 0 then writes the entry)
+__global__ void __launch_bounds__(256) bh_celltab_kernel(const BuildArgs a, const PubArgs pub) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= kNumCells) return;
     const uint32_t epoch = pub.er.get();
     const PartPlan* plan = pub.plan2 + (epoch & 1u);
     const PartPlan* plan_prev = pub.plan2 + ((epoch + 1u) & 1u);
-    if (c >= plan_prev->cut[pub.part] && c < plan_prev->cut[pub.part + 1]) {
+    if (lane == 0 && c >= plan_prev->cut[pub.part] && c < plan_prev->cut[pub.part + 1]) {
         const unsigned wk = pub.cellwork2[((epoch + 1u) & 1u) * kNumCells + c];
         for (int g = 0; g < pub.nparts; g++) reinterpret_cast<unsigned*>(pub.peers.a[g] + pub.off_workpub)[c] = wk;
     }
     if (c < plan->cut[pub.part] || c >= plan->cut[pub.part + 1]) return;
     const int n = build_n(a);
     const size_t stride = a.stride;
-    auto lb = [&](unsigned long long cell) {   // first sorted body whose cell index is >= cell
-        int lo = 0, hi = n;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((a.keys[mid] >> kCellShift) < cell) lo = mid + 1; else hi = mid; }
-        return lo;
-    };
-    const int first = lb(static_cast<unsigned long long>(c)), end = lb(static_cast<unsigned long long>(c) + 1ull);
+    // first sorted body whose cell index is >= c, and >= c + 1
+    const int first = warp_first_true(0, n, lane, [&](int i) { return (a.keys[i] >> kCellShift) >= static_cast<unsigned long long>(c); });
+    const int end = warp_first_true(first, n, lane, [&](int i) { return (a.keys[i] >> kCellShift) > static_cast<unsigned long long>(c); });
+    if (lane != 0) return;
     const int cnt = end - first;
     CellEntry en;
     en.M = en.MX = en.MY = 0.0; en.count = cnt; en.child = -1; en.x = en.y = en.m = 0.f; en.pad = 0;
@@ -2098,7 +2119,7 @@ static void bh_forces_partitioned(Engine& e, float theta, int nparts) {
             bh_emit_kernel<<<std::min(GE, e.num_sms * 8), T, 0, s>>>(ba, P.owner, P.status);
             PubArgs pa{peers, lay.off_celltab, lay.off_workpub, nparts, plan2, er, part_id(r),
                        reinterpret_cast<const unsigned*>(P.arena + lay.off_cellwork)};
-            bh_celltab_kernel<<<(kNumCells + 127) / 128, 128, 0, s>>>(ba, pa);
+            bh_celltab_kernel<<<kNumCells / 8, 256, 0, s>>>(ba, pa);   // one warp per cell
             e.ctr.kernel_launches += 8;
         }
     }
