@@ -378,6 +378,7 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
     ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop(t0, t1) if sampler else None
     ctr = lib.counters()
+    sort_levels_timed = ctr.get("bh_sort_levels")   # key levels the timed steps sorted on (the e2e leg below resets it: new set each step)
     if phases_in_timed_region:
         phases = lib.phase_ms()
     else:
@@ -498,7 +499,7 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
                     "pops_per_step": pops, "lanes_per_pop_histogram": hist,
                     "interactions_per_step": inter, "nodes_visited_per_step": vis, "tree_nodes": nodes,
                     "walk_ms_max_over_ranks": trav_max, "walk_imbalance_max_over_mean": (trav_max / (trav_all / world)) if trav_all > 0 else None,
-                    "theta": w["theta"], "sort_levels": lib.counters()["bh_sort_levels"]})
+                    "theta": w["theta"], "sort_levels": sort_levels_timed})
         if world > 1:
             # per-rank view of the partitioned step: bodies in each rank's domain part and its phase times
             mine = {"rank": rank, "part_bodies": lib.counters()["bh_part_bodies"], **{k: round(v, 4) for k, v in phases.items()},
