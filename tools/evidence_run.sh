@@ -18,5 +18,3 @@ for tool in memcheck racecheck synccheck; do
 done
 python tools/mode_costs.py > $O/r02_mode_costs.jsonl 2> $O/r02_mode_costs.err
 tail -2 $O/r02_mode_costs.jsonl
-python tools/c5_parity_probe.py > $O/r02_c5_parity_probe.jsonl 2> $O/r02_c5_parity_probe.err
-tail -c 600 $O/r02_c5_parity_probe.jsonl
