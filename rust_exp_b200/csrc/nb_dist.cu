@@ -191,7 +191,10 @@ void dist_fill_segments(Engine& e, AllPairsArgs& a) {
         if (e.mode == NBX_MODE_FAST) {
             a.flags = e.arena.flags(e.lay);  // the kernel's producer warp (or its stagers) wait per segment
             static const bool stage = [] { const char* v = getenv("NB_P2P_STAGE"); return v ? atoi(v) != 0 : true; }();
-            if (stage) {
+            // A rank without local bodies launches no force kernel (no items), so it must not count a staging epoch either:
+            // its stage counters would fall behind stage_want for good and the next staged step would wait for ever
+            // (found by tools/dist_check.py on 8 GPUs with a 20,000-body set: the last rank's shard is empty).
+            if (stage && local_count(e) > 0) {
                 // staged: each remote segment crosses NVLink once per step into the local mirror (2 stager CTAs per
                 // segment, inside the force kernel), then every j tile streams from local HBM
                 ensure_mirror(e);
