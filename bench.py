@@ -412,10 +412,9 @@ def measure(cx, name, steps, warmup, e2e_steps, with_cpu_baseline, sample_clocks
     torch.cuda.synchronize()
     e2e_s = cx.allreduce([time.perf_counter() - te0], "max")[0] / e2e_steps
     b, c = lib.dist_local_range() if world > 1 else (0, n)
-    if is3 and world > 1:   # rows of the nbx3 set: shards of ceil(n / 1024 / world) * 1024
-        shard = -(-(-(-n // 1024)) // world) * 1024
-        b = min(n, rank * shard)
-        c = min(n, b + shard) - b
+    if is3 and world > 1:   # rows of the nbx3 set this rank evaluates
+        from rust_exp_b200.dist import nbx3_local_rows
+        b, c = nbx3_local_rows(n, rank, world)
     h2d = int(cx.allreduce([4 * width * c], "sum")[0])
     d2h = h2d
     if is3 and world > 1:   # every rank uploads and reads back the whole nbx3 set

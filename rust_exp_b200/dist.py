@@ -55,6 +55,43 @@ class ShardLayout:
         return [(rank + q) % self.world for q in range(self.world)]
 
 
+def nbx3_shard_len(n: int, world: int) -> int:
+    """Rows per rank of the sharded nbx3 set (mirror of nb_3d.cu::x3_set): the set is padded to a multiple of 1,024 and
+    the 1,024-row tiles are dealt out evenly; world * shard rows is also the length of every rank's arrays (they are the
+    receive buffers of the in-place ncclAllGather)."""
+    n_pad = (max(n, 0) + 1023) // 1024 * 1024 + (1024 if n <= 0 else 0)
+    return (n_pad // 1024 + world - 1) // world * 1024
+
+
+def nbx3_local_rows(n: int, rank: int, world: int) -> tuple[int, int]:
+    """(begin, count) of the rows rank `rank` evaluates and integrates (mirror of nb_3d.cu::x3_step)."""
+    shard = nbx3_shard_len(n, world)
+    b = min(n, rank * shard)
+    return b, min(n, b + shard) - b
+
+
+def warp_first_true(lo: int, hi: int, pred, width: int = 32) -> tuple[int, int]:
+    """Mirror of nb_bh.cu::warp_first_true, the 32-ary search of the send / merge / cell-table kernels: first index in
+    [lo, hi) at which the monotone predicate (False..False True..True) holds, hi if none.  Every "lane" probes one
+    position per round and the first true lane narrows the range `width`-fold.  Returns (index, rounds)."""
+    rounds = 0
+    while hi - lo > width:
+        rounds += 1
+        step = (hi - lo + width - 1) // width
+        probes = [min(hi - 1, lo + (lane + 1) * step - 1) for lane in range(width)]
+        hits = [pred(p) for p in probes]
+        if not any(hits):
+            return hi, rounds
+        f = hits.index(True)
+        hi = probes[f] + 1
+        lo = lo + f * step
+    rounds += 1
+    for p in range(lo, min(hi, lo + width)):
+        if pred(p):
+            return p, rounds
+    return hi, rounds
+
+
 BODY_WEIGHT = 8  # nb_bh.cu kBodyWeight: build cost of one body in units of one walk pop
 
 

@@ -187,3 +187,74 @@ def test_partitioned_exchange_equals_global_stable_sort():
     assert merged_idx == [int(i) for i in ref]
     sizes = [len(part[0]) for part in out]
     assert sum(sizes) == n and max(sizes) - min(sizes) <= n // 8   # cell-granular balance
+
+
+# ---- the sharded nbx3 step (row shards + all-gather of the positions), host-side model over gloo -----------------------
+def _x3_accel(pos, m, rows, eps2=np.float32(1e-4)):
+    """f32 model of the nbx3 Newtonian law for the given rows against ALL bodies in ascending j (row-independent sums)."""
+    p = pos[rows]
+    dx = pos[None, :, 0] - p[:, None, 0]
+    dy = pos[None, :, 1] - p[:, None, 1]
+    dz = pos[None, :, 2] - p[:, None, 2]
+    d2 = dx * dx + dy * dy + dz * dz + eps2
+    w = (m[None, :] / (d2 * np.sqrt(d2))).astype(np.float32)
+    return np.stack([(w * dx).sum(1, dtype=np.float32), (w * dy).sum(1, dtype=np.float32), (w * dz).sum(1, dtype=np.float32)], 1)
+
+
+def _x3_worker(rank, world, port, n, steps, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rust_exp_b200.dist import nbx3_local_rows, nbx3_shard_len
+
+        fl = FakeLib(rank)
+        wire(fl, n, transport=0, nccl=True)                     # the sharded nbx3 path needs the communicator with ANY transport
+        assert ("nccl", b"U" * 128) in fl.log and fl.log[-1] == ("transport", 0)
+        s = ic.plummer_3d(n, seed=21)
+        shard = nbx3_shard_len(n, world)
+        b, c = nbx3_local_rows(n, rank, world)
+        pos = np.zeros((shard * world, 3), dtype=np.float32)    # every rank keeps ALL positions (the all-gather's receive buffer)
+        pos[:n] = s[:, :3]
+        vel = s[b:b + c, 3:6].copy()                            # velocities live with their rows
+        m = s[:, 6].copy()
+        dt = np.float32(0.01)
+        rows = np.arange(b, b + c)
+        for _ in range(steps):
+            a = _x3_accel(pos[:n], m, rows)
+            vel += dt * a
+            pos[b:b + c] += dt * vel
+            bufs = [torch.zeros(shard, 3) for _ in range(world)]
+            dist.all_gather(bufs, torch.from_numpy(pos[rank * shard:(rank + 1) * shard].copy()))   # in place on the device
+            pos = np.concatenate([t.numpy() for t in bufs])
+        outs = [None] * world
+        dist.all_gather_object(outs, (pos[:n].copy(), vel))
+        if rank == 0:
+            q.put(outs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [3000, 4096])
+def test_sharded_nbx3_step_equals_single_process(n):
+    """Rows sharded by index + one all-gather of the new positions per step == every row computed in one process, bit for
+    bit; every rank ends up with the same complete position set (the GPU version: tools/dist_check.py nbx3_sharded_*)."""
+    world, steps = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_x3_worker, args=(r, world, PORT[0], n, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    s = ic.plummer_3d(n, seed=21)
+    pos, vel, m, dt = s[:, :3].copy(), s[:, 3:6].copy(), s[:, 6].copy(), np.float32(0.01)
+    for _ in range(steps):
+        a = _x3_accel(pos, m, np.arange(n))
+        vel += dt * a
+        pos += dt * vel
+    assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))          # all ranks agree
+    assert np.array_equal(outs[0][0].view(np.uint32), pos.view(np.uint32))
+    assert np.array_equal(np.concatenate([o[1] for o in outs]).view(np.uint32), vel.view(np.uint32))

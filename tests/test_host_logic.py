@@ -131,3 +131,41 @@ def test_sfc_partition_properties():
             if n:
                 # never more than the ideal share plus one cell's worth of bodies
                 assert max(sizes) <= n / nparts + hist.max()
+
+
+# ---- round 2: mirrors of the 32-ary search and of the nbx3 row sharding ---------------------------------------------
+def test_warp_first_true_equals_bisection_and_needs_few_rounds():
+    import bisect
+    import random
+
+    from rust_exp_b200.dist import warp_first_true
+
+    rnd = random.Random(5)
+    for n in (0, 1, 31, 32, 33, 1000, 1024, 1025, 65536, 524288):
+        for _ in range(12):
+            keys = sorted(rnd.randrange(0, max(1, n // 3 + 1)) for _ in range(n))       # many ties
+            k = rnd.randrange(-1, max(1, n // 3 + 2))
+            for strict in (False, True):
+                pred = (lambda p: keys[p] > k) if strict else (lambda p: keys[p] >= k)
+                want = (bisect.bisect_right if strict else bisect.bisect_left)(keys, k)
+                got, rounds = warp_first_true(0, n, pred)
+                assert got == want
+                assert rounds <= 4 if n <= 32 ** 3 * 32 else True                          # 524,288 < 32^4: at most 4 rounds
+            lo = rnd.randrange(0, n + 1)
+            got, _ = warp_first_true(lo, n, lambda p: keys[p] >= k)                       # sub-range (the merge's second search)
+            assert got == max(lo, bisect.bisect_left(keys, k))
+
+
+def test_nbx3_row_shards_cover_the_set_in_whole_tiles():
+    from rust_exp_b200.dist import nbx3_local_rows, nbx3_shard_len
+
+    for n in (0, 1, 777, 1024, 5000, 20000, 65536, 1 << 20, (1 << 20) + 1):
+        for world in (1, 2, 3, 4, 8):
+            shard = nbx3_shard_len(n, world)
+            assert shard % 1024 == 0 and shard * world >= n
+            assert shard * world - max(n, 1) < 1024 * world + 1024                        # no more than one spare tile per rank
+            rows = [nbx3_local_rows(n, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and sum(c for _, c in rows) == n
+            for r in range(1, world):
+                assert rows[r][0] == min(n, rows[r - 1][0] + rows[r - 1][1]) or rows[r][1] == 0
+                assert rows[r][0] % 1024 == 0 or rows[r][1] == 0                          # shards start on tile boundaries
