@@ -7,8 +7,8 @@ section 8 before spending GPU time on them.
 
 Schemes:  morton32   32 consecutive bodies in Morton (key) order per warp            -- what the kernel does
           hilbert32  32 consecutive bodies in Hilbert order per warp
-          quarter8   Morton groups, but four independent 8-lane sub-stacks per warp: iterations = max over the quarters
-          hilbert_q8 both
+          half16 / quarter8 / eighth4   the same groups, but 2 / 4 / 8 independent sub-stacks of 16 / 8 / 4 lanes per
+                     warp: iterations = max over the sub-stacks (each load then touches 2 / 4 / 8 block addresses)
 A pop evaluates the four children of one opened node for the lanes of its mask; a lane that fails the reference's test
 s/d < theta on an interior child asks for it to be opened (rs-src/nbody.rs:333-377)."""
 import json
@@ -121,19 +121,25 @@ def main():
     out = {"n_bodies": int(len(leaves)), "theta": float(theta), "ic": "uniform disk (seed 4)", "tree_nodes": int(N), "schemes": {}}
     for oname, order in orders.items():
         gx, gy = bx[order], by[order]
-        pops32 = lanes32 = iters_q = pops_q = 0
+        pops32 = lanes32 = 0
+        sub = {16: [0, 0], 8: [0, 0], 4: [0, 0]}               # lanes per sub-stack -> [iterations, sub-pops]
         ngroups = (len(gx) + 31) // 32
         for g in range(ngroups):
             qx, qy = gx[32 * g:32 * g + 32], gy[32 * g:32 * g + 32]
             p, lp = walk_group(qx, qy, theta, K, X, Y, S, INTERIOR)
             pops32 += p
             lanes32 += lp
-            qp = [walk_group(qx[8 * k:8 * k + 8], qy[8 * k:8 * k + 8], theta, K, X, Y, S, INTERIOR)[0] for k in range(4) if len(qx) > 8 * k]
-            iters_q += max(qp)
-            pops_q += sum(qp)
+            for w in sub:
+                qp = [walk_group(qx[w * k:w * k + w], qy[w * k:w * k + w], theta, K, X, Y, S, INTERIOR)[0]
+                      for k in range(32 // w) if len(qx) > w * k]
+                sub[w][0] += max(qp)
+                sub[w][1] += sum(qp)
         out["schemes"][f"{oname}32"] = {"pops_per_group": pops32 / ngroups, "lane_efficiency": lanes32 / (32.0 * pops32)}
-        out["schemes"][f"{oname}_quarter8"] = {"iterations_per_group": iters_q / ngroups, "quarter_pops_per_group": pops_q / ngroups,
-                                               "balance_max_over_mean": iters_q / (pops_q / 4.0)}
+        for w, (it, sp) in sub.items():
+            name = {16: "half16", 8: "quarter8", 4: "eighth4"}[w]
+            out["schemes"][f"{oname}_{name}"] = {"iterations_per_group": it / ngroups, "sub_pops_per_group": sp / ngroups,
+                                                 "balance_max_over_mean": it / (sp / (32.0 / w)),
+                                                 "distinct_block_addresses_per_load": 32 // w}
     base = out["schemes"]["morton32"]["pops_per_group"]
     for k, v in out["schemes"].items():
         v["iterations_relative_to_morton32"] = (v.get("pops_per_group") or v.get("iterations_per_group")) / base
