@@ -57,7 +57,7 @@ def hilbert_index(ix, iy, bits):
     return d
 
 
-def walk_group(px, py, theta, K, X, Y, S, INTERIOR, record=None):
+def walk_group(px, py, theta, K, X, Y, S, INTERIOR, record=None, on_pop=None):
     """pops and lane-pops of one warp walking for the bodies (px, py); K[node] = its 4 children (array, -1 = none).
     record: optional list of per-lane lists that receive the nodes each lane interacts with, in evaluation order."""
     lanes = len(px)
@@ -68,6 +68,8 @@ def walk_group(px, py, theta, K, X, Y, S, INTERIOR, record=None):
         node, mask = stack.pop()
         pops += 1
         lane_pops += int(mask.sum())
+        if on_pop is not None and not first:
+            on_pop(node)                                      # the block popped holds the children of `node`
         ch = np.array([0, -1, -1, -1]) if first else K[node]
         first = False
         opens = []
@@ -94,7 +96,76 @@ def walk_group(px, py, theta, K, X, Y, S, INTERIOR, record=None):
     return pops, lane_pops
 
 
+def remote_pops_study(n, theta, nparts, cut_level=5):
+    """Domain-partitioned walk: which share of a rank's pops reads node blocks that live in ANOTHER
+    rank's memory, by depth below the cut -- i.e. what replicating the first k levels below the cut locally would save.
+    Parts = contiguous runs of cut-level cells in Morton order with equal body counts."""
+    s = ic.random_disk(n, seed=5)
+    o = oracle.get()
+    o.set_particles(s)
+    o.bh_build()
+    flat = o.bh_flatten()
+    kids = children_of(flat)
+    N = len(flat)
+    K = np.full((N, 4), -1, np.int64)
+    for i, k in enumerate(kids):
+        if k:
+            K[i, :len(k)] = k
+    X, Y = flat[:, 4].astype(f32), flat[:, 5].astype(f32)
+    S = (flat[:, 2] - flat[:, 0]).astype(f32)
+    INTERIOR = flat[:, 7] != 0
+    depth = flat[:, 8].astype(np.int64)
+    cell = np.full(N, -1, np.int64)          # DFS index of the node's ancestor at the cut level (-1: above the cut)
+    cur = -1
+    for i in range(N):                       # DFS pre-order: a cut-level node starts a new cell, deeper nodes inherit it
+        if depth[i] == cut_level:
+            cur = i
+        if depth[i] >= cut_level:
+            cell[i] = cur
+    body_leaf = (~INTERIOR) & (flat[:, 6] != 0)
+    leaves = np.nonzero(body_leaf)[0]
+    cells = np.unique(cell[cell >= 0])
+    count = {c: 0 for c in cells}
+    for l in leaves:
+        if cell[l] >= 0:
+            count[cell[l]] += 1
+    total = sum(count.values())
+    part_of_cell, acc = {}, 0
+    for c in cells:                          # Morton order = DFS order
+        part_of_cell[c] = min(nparts - 1, acc * nparts // max(total, 1))
+        acc += count[c]
+    part = np.array([part_of_cell[c] if c >= 0 else -1 for c in cell])
+    hist = {}                                # depth below the cut -> [local pops, remote pops]
+    top = [0]
+    ngroups = len(leaves) // 32
+    for g in range(0, ngroups, 4):           # every 4th group is plenty
+        sel = leaves[32 * g:32 * g + 32]
+        mine = part[sel[0]]
+
+        def on_pop(node, mine=mine):
+            if cell[node] < 0:
+                top[0] += 1
+                return
+            d = int(depth[node] - cut_level)
+            h = hist.setdefault(d, [0, 0])
+            h[1 if part[node] != mine else 0] += 1
+
+        walk_group(X[sel], Y[sel], theta, K, X, Y, S, INTERIOR, on_pop=on_pop)
+    allp = top[0] + sum(a + b for a, b in hist.values())
+    remote = sum(b for _, b in hist.values())
+    out = {"n_bodies": int(len(leaves)), "theta": float(theta), "parts": nparts, "cut_level": cut_level,
+           "pops_in_the_shared_top_tree": top[0] / allp, "remote_pops": remote / allp, "by_depth_below_cut": {}}
+    cum = 0
+    for d in sorted(hist):
+        cum += hist[d][1]
+        out["by_depth_below_cut"][d] = {"local": hist[d][0] / allp, "remote": hist[d][1] / allp,
+                                        "remote_pops_removed_by_replicating_down_to_here": cum / max(remote, 1)}
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[3].startswith("parts="):
+        return remote_pops_study(int(sys.argv[1]), f32(float(sys.argv[2])), int(sys.argv[3][6:]))
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
     theta = f32(float(sys.argv[2]) if len(sys.argv) > 2 else 0.5)
     s = ic.random_disk(n, seed=4)
